@@ -1,0 +1,177 @@
+/*
+ * nvf_b200.h - C ABI of the B200-native NVF leaf-block decoder hot path.
+ *
+ * This is the drop-in boundary for the ONE data-parallel path of huzi96/NVFPCC
+ * that this repository accelerates: the per-leaf-block Neural Volumetric Field
+ * decoder (forward for encode/decode; forward + rate-distortion loss + backward
+ * for train).  The reference has no FFI layer of its own - its boundary is the
+ * Python nn.Module pair
+ *     CompDecoder.forward(x, q)        utils/network.py:4758-4779
+ *     Net.forward / Net.reconstruct    NVFPCC.py:41-49
+ * plus the loss functions utils/loss.py:61-121 and the threshold idiom
+ * NVFPCC.py:631-637.  Each entry point below names the reference lines it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no torch types; all pointers are DEVICE pointers unless the
+ *     name ends in _host; all tensors fp32, contiguous, native PyTorch layout
+ *     (NCDHW; convT kernels (Cin,Cout,5,5,5); conv kernels (Cout,Cin,k,k,k)).
+ *   - "effective" weights: the caller applies the tiny parameter transforms
+ *     (kernel quantisation/noise + kernel_init, b + b_init, GDN reparam,
+ *     utils/network.py:606-620, gdn_3d.py:143-150) and passes the results.
+ *   - the library never allocates, frees or retains device memory: the caller
+ *     provides inputs, outputs and a workspace of nvf_workspace_bytes().
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     and performs no host synchronisation.
+ *   - return value: NVF_OK or a negative error code; nvf_strerror() decodes it.
+ *     Nothing throws or exits across this boundary.
+ */
+#ifndef NVF_B200_H_
+#define NVF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVF_ABI_VERSION 1
+
+enum {
+  NVF_OK = 0,
+  NVF_ERR_INVALID_ARG = -1,  /* NULL pointer, negative size, ...            */
+  NVF_ERR_UNSUPPORTED = -2,  /* channel configuration not compiled in       */
+  NVF_ERR_WORKSPACE = -3,    /* workspace too small                         */
+  NVF_ERR_CUDA = -4,         /* a CUDA runtime call failed (see nvf_last_cuda_error) */
+  NVF_ERR_NO_DEVICE = -5     /* no sm_100 device / kernel image not loadable */
+};
+
+/* Decoder geometry: latent channels `ch`, chanstr c0,c1,c2,c3
+ * (NVFPCC.py:34-39 Net.__init__, --ch / --chanstr). */
+typedef struct NvfDesc {
+  int32_t ch, c0, c1, c2, c3;
+} NvfDesc;
+
+/* Effective decoder tensors (device pointers).  Order follows
+ * CompDecoder.__init__, utils/network.py:4658-4751. */
+typedef struct NvfWeights {
+  const float* up0_w;   const float* up0_b;    /* (ch,c0,5,5,5), (c0)  convT s2 p2 op1 */
+  const float* igdn_beta; const float* igdn_gamma; /* (c0), (c0,c0) effective, gdn_3d.py:143-150 */
+  const float* conv0_w; const float* conv0_b;  /* (c0,c1,5,5,5), (c1)  convT s2 p2 op1 */
+  const float* up1_w;   const float* up1_b;    /* (c1,c2,5,5,5), (c2)  convT s2 p0     */
+  const float* conv1_w; const float* conv1_b;  /* (c2,c2,4,4,4), (c2)  conv  k4 p0     */
+  const float* up2_w;   const float* up2_b;    /* (c2,c3,5,5,5), (c3)  convT s2 p0     */
+  const float* conv2_w; const float* conv2_b;  /* (c3,c3,4,4,4), (c3)  conv  k4 p0     */
+  const float* cls2_w;  const float* cls2_b;   /* (1,c3,3,3,3), (1)    conv2_cls       */
+  const float* cls1_w;  const float* cls1_b;   /* (1,c2,3,3,3), (1)    conv1_cls; NULL ok for decode */
+  const float* cls0_w;  const float* cls0_b;   /* (1,c1,3,3,3), (1)    conv0_cls; NULL ok for decode */
+} NvfWeights;
+
+/* Gradients w.r.t. the effective tensors, same shapes as NvfWeights. */
+typedef struct NvfWeightGrads {
+  float* up0_w;   float* up0_b;
+  float* igdn_beta; float* igdn_gamma;
+  float* conv0_w; float* conv0_b;
+  float* up1_w;   float* up1_b;
+  float* conv1_w; float* conv1_b;
+  float* up2_w;   float* up2_b;
+  float* conv2_w; float* conv2_b;
+  float* cls2_w;  float* cls2_b;
+  float* cls1_w;  float* cls1_b;
+  float* cls0_w;  float* cls0_b;
+} NvfWeightGrads;
+
+enum { NVF_MODE_DECODE = 0, NVF_MODE_TRAIN = 1 };
+
+int nvf_abi_version(void);
+const char* nvf_strerror(int code);
+/* cudaError_t of the last failing CUDA call on this thread (0 if none). */
+int nvf_last_cuda_error(void);
+/* 1 if a fused (single-kernel, activations on chip) decode kernel exists for desc. */
+int nvf_has_fused_decode(const NvfDesc* desc);
+
+/* Workspace size for a call with `n_blocks` leaf blocks in `mode`. */
+int nvf_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, int mode, size_t* bytes_out);
+
+/*
+ * Decode: latents -> occupancy -> points.  Replaces the per-block loop of
+ * decode(), NVFPCC.py:625-638 (net.reconstruct -> to_sparse -> `F > thh`
+ * pruning -> coords + origin) and the same idiom in encode(), :516-539, by ONE
+ * batched call.
+ *   latent     [n_blocks, ch, 2,2,2]   rounded latents (NVFPCC.py:604-607)
+ *   origins    [n_blocks, 3] int32 leaf origins or NULL (then coords are in-block)
+ *   thh        strict threshold on the sigmoid probability (NVFPCC.py:632)
+ *   prob_out   [n_blocks,1,32,32,32] or NULL  - dense probabilities (`out_dense`)
+ *   mask_out   [n_blocks,1024] uint32 or NULL - bit k of word (i*32+j) = p[i,j,k] > thh
+ *   counts_out [n_blocks] int32               - points per block
+ *   coords_out [cap,3] int32 or NULL          - origin + (i,j,k), block order then
+ *                                               row-major (i,j,k) order
+ *   total_out  [1] int64                      - total number of points (may exceed cap;
+ *                                               only the first cap are written)
+ */
+int nvf_decode(const NvfDesc* desc, const NvfWeights* w, const float* latent, const int32_t* origins,
+               int64_t n_blocks, float thh, float* prob_out, uint32_t* mask_out, int32_t* counts_out,
+               int32_t* coords_out, int64_t cap, int64_t* total_out, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/*
+ * Second half of nvf_decode on its own: occupancy masks + counts -> ordered
+ * points (used when the caller's first `cap` was too small).  Workspace:
+ * (n_blocks+1) * 8 bytes.  Replaces NVFPCC.py:631-637 like nvf_decode.
+ */
+int nvf_emit_points(const uint32_t* mask, const int32_t* counts, const int32_t* origins, int64_t n_blocks,
+                    int32_t* coords_out, int64_t cap, int64_t* total_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
+ * Training forward (CompDecoder.forward in train mode incl. aux heads,
+ * utils/network.py:4758-4768): writes probabilities of the three heads and
+ * keeps every activation needed by nvf_train_backward in `workspace`.
+ *   out  [n,1,32,32,32], cls1 [n,1,16,16,16], cls0 [n,1,8,8,8]
+ */
+int nvf_train_forward(const NvfDesc* desc, const NvfWeights* w, const float* latent, int64_t n_blocks, float* out,
+                      float* cls1, float* cls0, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Distortion losses + metrics + gradient seeds.  Replaces MultiscaleProcessor
+ * (NVFPCC.py:76-88), get_surf_focal_dense (utils/loss.py:94-111, beta=1,
+ * alpha=alpha_main), get_focal_dense x2 (utils/loss.py:61-72, alpha=alpha_aux),
+ * get_sse1 / get_acc_dense (utils/loss.py:74-84,113-121).
+ *   gt [n,1,32,32,32] fp32 0/1, dist [n,1,32,32,32] fp32
+ *   sums_out [16] float64: 0 bce, 1 ms0 (8^3 head), 2 ms1 (16^3 head),
+ *     3 sse(thh_metric), 4 denom, 5..8 tp,ap,tn,an main head (thh 0.5),
+ *     9..12 tp,ap,tn,an 8^3 head, 13..16 -> see NVF_LOSS_SUMS
+ *   g_out/g_cls1/g_cls0: dLoss/dprobability * 1 (same shapes as the heads) or
+ *     NULL; when given they are the seeds nvf_train_backward consumes.
+ */
+#define NVF_LOSS_SUMS 20
+int nvf_loss_seeds(const float* out, const float* cls1, const float* cls0, const float* gt, const float* dist,
+                   int64_t n_blocks, float alpha_main, float alpha_aux, float thh_metric, double* sums_out,
+                   float* g_out, float* g_cls1, float* g_cls0, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/*
+ * Training backward: given dLoss/dprobability of the three heads, accumulates
+ * dLoss/d(effective weights) and writes dLoss/d(latent).  Replaces autograd
+ * through CompDecoder.forward.
+ *   g_out/g_cls1/g_cls0  gradients w.r.t. the sigmoid outputs (NULL = zero)
+ *   flags: NVF_BWD_WGRAD compute weight grads (else skipped, NVFPCC.py:225-251
+ *          discards them), NVF_BWD_DLATENT compute d_latent (NVFPCC.py:149-223
+ *          discards it).  Weight-gradient buffers are OVERWRITTEN.
+ */
+enum { NVF_BWD_WGRAD = 1, NVF_BWD_DLATENT = 2 };
+int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* latent, int64_t n_blocks,
+                       const float* g_out, const float* g_cls1, const float* g_cls0, int flags,
+                       const NvfWeightGrads* gw, float* g_latent, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* FP32 FFMA throughput micro-benchmark (roofline denominator):
+ * runs `iters` dependent-chain FFMA batches on every SM; returns the number of
+ * FLOPs executed in flops_out.  The caller times it with CUDA events. */
+int nvf_ffma_microbench(int variant, int64_t iters, float* sink /*[>= 148*1024]*/, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVF_B200_H_ */

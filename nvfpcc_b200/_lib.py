@@ -1,0 +1,258 @@
+"""ctypes binding of the C ABI in include/nvf_b200.h.
+
+The product library is `nvfpcc_b200/libnvf_b200.so` (built in-tree by
+`__graft_entry__.build()` / `nvfpcc_b200/build.py` with nvcc for sm_100a).
+There is no CPU fallback: `cuda_binding()` raises if the library is missing or
+cannot be loaded, and every op in `nvfpcc_b200.ops` requires CUDA tensors.
+
+`Binding` itself is device-agnostic plumbing (it passes `tensor.data_ptr()`), so
+the test suite can also point it at the test-only emulator build under
+tests/emu/ to check kernel logic on CPU tensors; the package never does that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libnvf_b200.so"
+
+WEIGHT_FIELDS = (
+    "up0_w", "up0_b", "igdn_beta", "igdn_gamma", "conv0_w", "conv0_b", "up1_w", "up1_b", "conv1_w", "conv1_b",
+    "up2_w", "up2_b", "conv2_w", "conv2_b", "cls2_w", "cls2_b", "cls1_w", "cls1_b", "cls0_w", "cls0_b",
+)
+NVF_MODE_DECODE, NVF_MODE_TRAIN = 0, 1
+NVF_BWD_WGRAD, NVF_BWD_DLATENT = 1, 2
+NVF_LOSS_SUMS = 20
+EXPORTS = (
+    "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_has_fused_decode", "nvf_workspace_bytes",
+    "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
+    "nvf_ffma_microbench",
+)
+
+
+class NvfDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("ch", "c0", "c1", "c2", "c3")]
+
+
+class NvfWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+class NvfWeightGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+def weight_shapes(ch: int, channels: Sequence[int]) -> Dict[str, tuple]:
+    c0, c1, c2, c3 = (int(c) for c in channels)
+    return {
+        "up0_w": (ch, c0, 5, 5, 5), "up0_b": (c0,), "igdn_beta": (c0,), "igdn_gamma": (c0, c0),
+        "conv0_w": (c0, c1, 5, 5, 5), "conv0_b": (c1,), "up1_w": (c1, c2, 5, 5, 5), "up1_b": (c2,),
+        "conv1_w": (c2, c2, 4, 4, 4), "conv1_b": (c2,), "up2_w": (c2, c3, 5, 5, 5), "up2_b": (c3,),
+        "conv2_w": (c3, c3, 4, 4, 4), "conv2_b": (c3,), "cls2_w": (1, c3, 3, 3, 3), "cls2_b": (1,),
+        "cls1_w": (1, c2, 3, 3, 3), "cls1_b": (1,), "cls0_w": (1, c1, 3, 3, 3), "cls0_b": (1,),
+    }
+
+
+class NvfError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Binding:
+    """Thin, typed wrapper over one loaded shared library exporting the NVF C ABI."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        for name in EXPORTS:
+            if not hasattr(L, name):
+                raise NvfError("%s does not export %s" % (path, name))
+        L.nvf_abi_version.restype = C.c_int
+        L.nvf_strerror.restype = C.c_char_p
+        L.nvf_strerror.argtypes = [C.c_int]
+        L.nvf_last_cuda_error.restype = C.c_int
+        L.nvf_has_fused_decode.argtypes = [C.POINTER(NvfDesc)]
+        L.nvf_workspace_bytes.argtypes = [C.POINTER(NvfDesc), C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
+        vp = C.c_void_p
+        L.nvf_decode.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfWeights), vp, vp, C.c_int64, C.c_float, vp, vp, vp,
+                                 vp, C.c_int64, vp, vp, C.c_size_t, vp]
+        L.nvf_emit_points.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_size_t, vp]
+        L.nvf_train_forward.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfWeights), vp, C.c_int64, vp, vp, vp, vp,
+                                        C.c_size_t, vp]
+        L.nvf_loss_seeds.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,
+                                     vp, C.c_size_t, vp]
+        L.nvf_train_backward.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfWeights), vp, C.c_int64, vp, vp, vp, C.c_int,
+                                         C.POINTER(NvfWeightGrads), vp, vp, C.c_size_t, vp]
+        L.nvf_ffma_microbench.argtypes = [C.c_int, C.c_int64, vp, C.POINTER(C.c_double), vp]
+        if L.nvf_abi_version() != 1:
+            raise NvfError("ABI version mismatch in %s" % path)
+        self._ws: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ utils
+    def check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.nvf_strerror(rc).decode()
+            raise NvfError("%s failed: %s (rc=%d, cudaError=%d)" % (what, msg, rc, self.lib.nvf_last_cuda_error()))
+
+    @staticmethod
+    def desc(ch: int, channels: Sequence[int]) -> NvfDesc:
+        c0, c1, c2, c3 = (int(c) for c in channels)
+        return NvfDesc(int(ch), c0, c1, c2, c3)
+
+    @staticmethod
+    def _stream(dev: torch.device):
+        if dev.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        return None
+
+    def workspace_bytes(self, desc: NvfDesc, n: int, mode: int) -> int:
+        out = C.c_size_t(0)
+        self.check(self.lib.nvf_workspace_bytes(C.byref(desc), n, mode, C.byref(out)), "nvf_workspace_bytes")
+        return int(out.value)
+
+    def cached_workspace(self, nbytes: int, dev: torch.device, tag: str) -> torch.Tensor:
+        """Grow-only scratch buffer per (device, tag); contents need not survive between calls."""
+        key = (str(dev), tag)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+            self._ws[key] = buf
+        return buf
+
+    @staticmethod
+    def pack_weights(weights: Dict[str, torch.Tensor], dev: torch.device, need_aux: bool):
+        keep = []
+        st = NvfWeights()
+        for name in WEIGHT_FIELDS:
+            t = weights.get(name)
+            if t is None:
+                if need_aux or not name.startswith(("cls1", "cls0")):
+                    raise NvfError("missing effective tensor " + name)
+                setattr(st, name, None)
+                continue
+            if t.device != dev or t.dtype != torch.float32:
+                raise NvfError("%s must be float32 on %s" % (name, dev))
+            t = t.detach().contiguous()
+            keep.append(t)
+            setattr(st, name, t.data_ptr())
+        return st, keep
+
+    # ------------------------------------------------------------------ calls
+    def decode(self, desc: NvfDesc, weights: Dict[str, torch.Tensor], latent: torch.Tensor,
+               origins: Optional[torch.Tensor], thh: float, want_prob: bool = False, want_coords: bool = True,
+               cap: Optional[int] = None):
+        dev = latent.device
+        n = int(latent.shape[0])
+        latent = latent.detach().contiguous().float()
+        wst, keep = self.pack_weights(weights, dev, need_aux=False)
+        if origins is not None:
+            origins = origins.to(device=dev, dtype=torch.int32).contiguous()
+        nbytes = self.workspace_bytes(desc, n, NVF_MODE_DECODE)
+        ws = self.cached_workspace(nbytes, dev, "decode")
+        prob = torch.empty((n, 1, 32, 32, 32), dtype=torch.float32, device=dev) if want_prob else None
+        mask = torch.empty((n, 1024), dtype=torch.int32, device=dev)
+        counts = torch.empty((n,), dtype=torch.int32, device=dev)
+        total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        if cap is None:
+            cap = n * 2048
+        coords = torch.empty((cap, 3), dtype=torch.int32, device=dev) if want_coords else None
+        rc = self.lib.nvf_decode(C.byref(desc), C.byref(wst), _ptr(latent), _ptr(origins), n, float(thh), _ptr(prob),
+                                 _ptr(mask), _ptr(counts), _ptr(coords), cap if want_coords else 0, _ptr(total),
+                                 _ptr(ws), nbytes, self._stream(dev))
+        self.check(rc, "nvf_decode")
+        del keep
+        res = dict(prob=prob, mask=mask, counts=counts, total=total, coords=None)
+        if want_coords:
+            k = int(total.item())  # the one host sync of the decode path: size of the result
+            if k > cap:
+                coords = torch.empty((k, 3), dtype=torch.int32, device=dev)
+                rc = self.lib.nvf_emit_points(_ptr(mask), _ptr(counts), _ptr(origins), n, _ptr(coords), k, _ptr(total),
+                                              _ptr(ws), nbytes, self._stream(dev))
+                self.check(rc, "nvf_emit_points")
+            res["coords"] = coords[:k]
+        return res
+
+    def train_forward(self, desc: NvfDesc, weights: Dict[str, torch.Tensor], latent: torch.Tensor):
+        dev = latent.device
+        n = int(latent.shape[0])
+        latent = latent.detach().contiguous().float()
+        wst, keep = self.pack_weights(weights, dev, need_aux=True)
+        nbytes = self.workspace_bytes(desc, n, NVF_MODE_TRAIN)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)  # owned by the autograd node until backward
+        out = torch.empty((n, 1, 32, 32, 32), dtype=torch.float32, device=dev)
+        cls1 = torch.empty((n, 1, 16, 16, 16), dtype=torch.float32, device=dev)
+        cls0 = torch.empty((n, 1, 8, 8, 8), dtype=torch.float32, device=dev)
+        rc = self.lib.nvf_train_forward(C.byref(desc), C.byref(wst), _ptr(latent), n, _ptr(out), _ptr(cls1),
+                                        _ptr(cls0), _ptr(ws), nbytes, self._stream(dev))
+        self.check(rc, "nvf_train_forward")
+        return out, cls1, cls0, ws, keep
+
+    def train_backward(self, desc: NvfDesc, weights: Dict[str, torch.Tensor], latent: torch.Tensor, ws: torch.Tensor,
+                       g_out, g_cls1, g_cls0, need_wgrad: bool, need_dlatent: bool):
+        dev = latent.device
+        n = int(latent.shape[0])
+        latent = latent.detach().contiguous().float()
+        wst, keep = self.pack_weights(weights, dev, need_aux=True)
+        grads: Dict[str, torch.Tensor] = {}
+        gst = NvfWeightGrads()
+        if need_wgrad:
+            for name in WEIGHT_FIELDS:
+                g = torch.empty_like(weights[name], memory_format=torch.contiguous_format)
+                grads[name] = g
+                setattr(gst, name, g.data_ptr())
+        g_latent = torch.empty_like(latent) if need_dlatent else None
+        flags = (NVF_BWD_WGRAD if need_wgrad else 0) | (NVF_BWD_DLATENT if need_dlatent else 0)
+        cg = [None if g is None else g.detach().contiguous().float() for g in (g_out, g_cls1, g_cls0)]
+        rc = self.lib.nvf_train_backward(C.byref(desc), C.byref(wst), _ptr(latent), n, _ptr(cg[0]), _ptr(cg[1]),
+                                         _ptr(cg[2]), flags, C.byref(gst), _ptr(g_latent), _ptr(ws), ws.numel(),
+                                         self._stream(dev))
+        self.check(rc, "nvf_train_backward")
+        del keep, cg
+        return g_latent, grads
+
+    def loss_seeds(self, out, cls1, cls0, gt, dist, alpha_main=0.9, alpha_aux=0.85, thh_metric=0.6,
+                   want_seeds: bool = True):
+        dev = out.device
+        n = int(out.shape[0])
+        ts = [t.detach().contiguous().float() for t in (out, cls1, cls0, gt, dist)]
+        sums = torch.zeros((NVF_LOSS_SUMS,), dtype=torch.float64, device=dev)
+        ws = self.cached_workspace(8 * NVF_LOSS_SUMS * (n + 1), dev, "loss")
+        g = [torch.empty_like(t) for t in ts[:3]] if want_seeds else [None, None, None]
+        rc = self.lib.nvf_loss_seeds(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), n,
+                                     float(alpha_main), float(alpha_aux), float(thh_metric), _ptr(sums), _ptr(g[0]),
+                                     _ptr(g[1]), _ptr(g[2]), _ptr(ws), ws.numel(), self._stream(dev))
+        self.check(rc, "nvf_loss_seeds")
+        return sums, g
+
+    def ffma_microbench(self, variant: int, iters: int, sink: torch.Tensor) -> float:
+        flops = C.c_double(0)
+        rc = self.lib.nvf_ffma_microbench(variant, iters, _ptr(sink), C.byref(flops), self._stream(sink.device))
+        self.check(rc, "nvf_ffma_microbench")
+        return float(flops.value)
+
+
+_cuda_binding: Optional[Binding] = None
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, LIB_NAME)
+
+
+def cuda_binding() -> Binding:
+    """The product binding.  Fails loudly when the CUDA library is not built."""
+    global _cuda_binding
+    if _cuda_binding is None:
+        p = lib_path()
+        if not os.path.isfile(p):
+            raise NvfError("%s not found: build it with `python -m nvfpcc_b200.build` (nvcc, sm_100a). "
+                           "There is no CPU fallback." % p)
+        _cuda_binding = Binding(p)
+    return _cuda_binding
