@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""Benchmark of the NVF leaf-block decoder hot path (BASELINE.json metric:
+"NVF decoded voxels/sec & train blocks/sec at 1/2/4/8 B200; % of roofline").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Primary line = BASELINE.json configs[1]: weight-loop training steps
+(NVFPCC.py:149-223) at batchsize 16 on synthetic vox10 leaf blocks, lambda 200,
+lr 1e-3, chanstr 8,16,8,8 -> train blocks/s.  The same JSON line carries the
+decode half of the metric under "decode" (all 1247 vox10 blocks, thh 0.65 ->
+decoded voxels/s), each with its own roofline / e2e numbers.
+
+A "step" is one pass of the hot path over one batch: train = forward + fused
+rate-distortion loss + backward + Adam on 16 blocks per rank; decode = all of
+the rank's blocks through the fused decode kernel to an ordered point list.
+`value` is measured with inputs resident in HBM; `e2e` goes through the public
+API with pinned HOST buffers (H2D of the step's inputs and D2H of its result
+inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+# algorithmic work per block, SURVEY.md section 8(d) / BASELINE.md section 3
+F_DEC = {"8,16,8,8": 398_481_616, "16,32,16,16": 1_567_314_848}
+F_TRAIN = {"8,16,8,8": 1_201_139_184, "16,32,16,16": 4_713_333_216}
+FP32_PEAK_THEORETICAL = 148 * 128 * 2 * 1.965e9 / 1e12   # TFLOP/s at the 1965 MHz max clock
+HP = dict(lmbda=200.0, w1=10.0, w2=57.0, lr=1e-3, batch=16, thh=0.65)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--chanstr", default="8,16,8,8")
+    ap.add_argument("--resolution", type=int, default=1024, help="1024 = vox10, 2048 = vox11")
+    ap.add_argument("--train-blocks", type=int, default=128, help="distinct leaf blocks (per rank) cycled by the train steps")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-steps", type=int, default=5)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- data
+def make_cloud(resolution):
+    from nvfpcc_b200 import synth
+    pts = synth.sphere_shell_points(resolution)
+    return pts, synth.leaf_origins(pts)
+
+
+def make_net(chanstr, device):
+    from nvfpcc_b200 import network, synth
+    network.set_seed(synth.synthetic_seed())
+    return network.Net(None, "Gaussian", ch=3, channel_str=chanstr).to(device)
+
+
+def calibrate_threshold_bias(net, latents, thh, target_occ=0.021, sample=64):
+    """Random-init weights never cross thh: shift conv2_cls.b so that the
+    (1 - target_occ) quantile of p equals thh, giving a realistic ~2 % occupancy."""
+    with torch.no_grad():
+        p = net.reconstruct(latents[:sample], 2)
+        logit = torch.log(p) - torch.log1p(-p)
+        qv = torch.quantile(logit.flatten()[:: 7].float(), 1 - target_occ)
+        want = float(np.log(thh / (1 - thh)))
+        net.reconstructor.conv2_cls.b += (want - qv)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self.f.name)
+        return out
+
+
+# ----------------------------------------------------------------------------- timing helpers
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed(fn, steps, world, pre=None):
+    """device time (CUDA events on the launching stream) of `steps` calls, summed over the calls
+    (an optional untimed `pre` hook - the L2 flush - runs before each), max over ranks, in ms."""
+    barrier_sync(world)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        if pre is not None:
+            pre()
+        ev[i][0].record()
+        fn(i)
+        ev[i][1].record()
+    barrier_sync(world)
+    return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world)
+
+
+def flush_l2(buf):
+    buf.add_(1.0)  # 512 MB read+write: larger than the 126 MB L2
+
+
+def ffma_peak(binding):
+    sink = torch.empty(148 * 4 * 256 * 2, device="cuda")
+    best = {}
+    for variant in (0, 1):
+        for _ in range(2):
+            binding.ffma_microbench(variant, 2000, sink)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flops = binding.ffma_microbench(variant, 40000, sink)
+        e1.record()
+        torch.cuda.synchronize()
+        best["ffma" if variant == 0 else "ffma2"] = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return best
+
+
+# ----------------------------------------------------------------------------- workloads
+class TrainWorkload:
+    """Weight-loop steps of train() (NVFPCC.py:149-223) on the fused path."""
+
+    def __init__(self, args, rank, world, pts, origins):
+        from nvfpcc_b200 import synth
+        self.args, self.rank, self.world = args, rank, world
+        nb = min(args.train_blocks, origins.shape[0])
+        sel = (np.arange(nb) + rank * nb) % origins.shape[0]
+        gt, dist_ = synth.gt_and_dist(pts, origins[sel])
+        self.n_total = float(pts.shape[0])
+        self.gt_host = torch.from_numpy(gt).float().pin_memory()
+        self.dist_host = torch.from_numpy(dist_).float().pin_memory()
+        self.gt_dev = self.gt_host.cuda()
+        self.dist_dev = self.dist_host.cuda()
+        self.nb = nb
+        self.net = make_net(args.chanstr, "cuda")
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=HP["lr"])
+        self.emb = torch.ones(nb, 3, 2, 2, 2, device="cuda", requires_grad=True)
+        self.B = HP["batch"]
+        self.last_loss = None
+
+    def batch_idx(self, i):
+        s = (i * self.B) % self.nb
+        return (torch.arange(self.B) + s) % self.nb
+
+    def step(self, i, host_inputs):
+        from nvfpcc_b200 import dist as D
+        from nvfpcc_b200 import ops
+        idx = self.batch_idx(i)
+        if host_inputs:
+            gt = self.gt_host[idx].pin_memory().cuda(non_blocking=True)
+            dst = self.dist_host[idx].pin_memory().cuda(non_blocking=True)
+        else:
+            gt, dst = self.gt_dev[idx.cuda()], self.dist_dev[idx.cuda()]
+        self.opt.zero_grad(set_to_none=True)
+        n_pts = D.allreduce_sum_(gt.sum())                       # batch-global (NVFPCC.py:154,161)
+        out, cls_list, net_bits, latent_bits = self.net(self.emb[idx.cuda()], "train", 1)
+        bce, ms0, ms1, _ = ops.rd_distortion(out, cls_list[1], cls_list[0], gt, dst, 0.9, 0.85, 0.6)
+        bpp_loss = latent_bits.sum() / n_pts * HP["w1"] + net_bits.sum() / self.n_total * HP["w2"]
+        loss = bce + ms0 + ms1 + HP["lmbda"] * bpp_loss
+        loss.backward()
+        D.allreduce_grads_(self.net.parameters())                # ONE NCCL all-reduce of the shared weights
+        self.opt.step()
+        if host_inputs:
+            self.last_loss = loss.item()                         # D2H of the step's result
+        else:
+            self.last_loss = loss
+        return loss
+
+    h2d_bytes = 2 * 16 * 32768 * 4
+    d2h_bytes = 4
+
+
+class DecodeWorkload:
+    """All leaf blocks of the cloud through the fused decode kernel (NVFPCC.py:625-638 batched)."""
+
+    def __init__(self, args, rank, world, pts, origins):
+        from nvfpcc_b200 import dist as D
+        from nvfpcc_b200 import synth
+        self.rank, self.world = rank, world
+        self.n_all = origins.shape[0]
+        lo, hi = D.block_range(self.n_all, rank, world)
+        lat = synth.random_latents(self.n_all, 3, seed=0)
+        self.lat_host = torch.from_numpy(lat[lo:hi]).pin_memory()
+        self.org_host = torch.from_numpy(origins[lo:hi].astype(np.int32)).pin_memory()
+        self.lat_dev, self.org_dev = self.lat_host.cuda(), self.org_host.cuda()
+        self.net = make_net(args.chanstr, "cuda")
+        calibrate_threshold_bias(self.net, torch.from_numpy(lat).cuda(), HP["thh"])
+        self.n_local = hi - lo
+        self.points = 0
+
+    def step(self, i, host_inputs):
+        from nvfpcc_b200 import dist as D
+        if host_inputs:
+            r = self.net.decode_points(self.lat_host, self.org_host, HP["thh"], return_host=False)
+            c, n = D.gather_points(r["coords"], r["counts"])     # coordinate gather to rank 0
+            if c is not None:
+                c_host = c.cpu()
+                self.points = c_host.shape[0]
+        else:
+            r = self.net.decode_points(self.lat_dev, self.org_dev, HP["thh"], return_host=False)
+            self.points = r["coords"].shape[0]
+        return r
+
+
+# ----------------------------------------------------------------------------- reference arm
+def oracle_state(chanstr):
+    from nvfpcc_b200 import synth
+    from oracle import nvf_oracle as O
+    return O.make_state(3, [int(c) for c in chanstr.split(",")], synth.synthetic_seed())
+
+
+def cpu_train_baseline(args, pts, origins, budget_s=20.0, max_steps=None):
+    """The reference algorithm (oracle port, torch CPU fp32, all host threads) on the same train
+    workload: one weight-loop step = forward + losses + backward + Adam at batch 16."""
+    from nvfpcc_b200 import synth
+    from oracle import nvf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.clone() for k, v in oracle_state(args.chanstr).items() if not k.startswith("_")}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if not k.endswith(("_init", "pedestal"))}
+    opt = torch.optim.Adam(list(params.values()), lr=HP["lr"])
+    B = HP["batch"]
+    gt, dist_ = synth.gt_and_dist(pts, origins[:B])
+    gt, dist_ = torch.from_numpy(gt).float(), torch.from_numpy(dist_).float()
+    emb = torch.ones(B, 3, 2, 2, 2, requires_grad=True)
+    n_total = float(pts.shape[0])
+
+    def one():
+        opt.zero_grad()
+        res = O.net_forward(emb, sd, "train", 1)
+        L = O.train_loss(res, gt, dist_, gt.sum(), n_total, HP["lmbda"], HP["w1"], HP["w2"])
+        L["loss"].backward()
+        opt.step()
+
+    one()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one()
+        n += 1
+        el = time.perf_counter() - t0
+        if (max_steps and n >= max_steps) or (not max_steps and (el > budget_s or n >= 64)):
+            break
+    return dict(value=n * B / el, unit="blocks/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d weight-loop steps at batch %d (%.1f s) of the oracle port, torch CPU fp32" % (n, B, el)), el / n
+
+
+def cpu_decode_baseline(args, origins, budget_s=12.0):
+    """decode() as shipped: one block per iteration, batch 1 (NVFPCC.py:625-638)."""
+    from nvfpcc_b200 import synth
+    from oracle import nvf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v for k, v in oracle_state(args.chanstr).items() if not k.startswith("_")}
+    lat = torch.from_numpy(synth.random_latents(256, 3, seed=0))
+    n = 0
+    with torch.no_grad():
+        O.reconstruct(lat[:1], sd, 2)
+        t0 = time.perf_counter()
+        while n < 256:
+            p = O.reconstruct(lat[n:n + 1], sd, 2)
+            O.threshold_points(p, origins[n:n + 1], HP["thh"])
+            n += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        el = time.perf_counter() - t0
+    return dict(value=n * 32768 / el, unit="voxels/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d blocks at batch 1 (%.1f s) of the oracle port, torch CPU fp32" % (n, el))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, origins = make_cloud(args.resolution)
+    cb, sec_per = cpu_train_baseline(args, pts, origins, max_steps=(args.steps + args.warmup))
+    dec = cpu_decode_baseline(args, origins)
+    line = dict(impl="reference", metric="train_blocks_per_sec", value=cb["value"], unit="blocks/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec_per * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=workload_config(args, args.gpus), cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit="blocks/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                decode=dict(metric="decoded_voxels_per_sec", value=dec["value"], unit="voxels/s", cpu_baseline=dec,
+                            e2e=dict(value=dec["value"], unit="voxels/s", h2d_bytes_per_step=0,
+                                     d2h_bytes_per_step=0)))
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "NVFPCC.py train weight-loop steps on synthetic vox%d sphere-shell leaf blocks, batchsize 16 per GPU, "
+                        "lambda=200 w1=10 w2=57 lr=1e-3 q=1, chanstr %s ch=3 (BASELINE.json configs[1])"
+                        % (10 if args.resolution == 1024 else 11, args.chanstr),
+            "chanstr": args.chanstr, "ch": 3, "batch_per_gpu": HP["batch"], "global_batch": HP["batch"] * world,
+            "parallelism": "block-sharded dp%d, NCCL all-reduce of shared-weight grads" % world,
+            "l2": "512 MB buffer rewritten between timed steps (flush)"}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    from nvfpcc_b200 import _lib
+    rank, world, local = dist_setup(args.gpus)
+    binding = _lib.cuda_binding()
+    pts, origins = make_cloud(args.resolution)
+    flush = torch.zeros(128 * 1024 * 1024, device="cuda")
+    sampler = ClockSampler(local)
+
+    # ---------------- train (primary) ----------------
+    tw = TrainWorkload(args, rank, world, pts, origins)
+    for i in range(args.warmup):
+        tw.step(i, False)
+    launches0 = binding.launch_count()
+    if rank == 0:
+        sampler.start()
+
+    ms_total = timed(lambda i: tw.step(args.warmup + i, False), args.steps, world, pre=lambda: flush_l2(flush))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = binding.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    train_value = HP["batch"] * world / (ms_step * 1e-3)
+    for i in range(2):
+        tw.step(i, True)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tw.step(args.warmup + i, True)
+    barrier_sync(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
+    train_e2e = HP["batch"] * world / (e2e_ms * 1e-3)
+
+    # ---------------- decode (second half of the metric) ----------------
+    dw = DecodeWorkload(args, rank, world, pts, origins)
+    for i in range(3):
+        dw.step(i, False)
+    dl0 = binding.launch_count()
+
+    dms_total = timed(lambda i: dw.step(i, False), args.decode_steps, world, pre=lambda: flush_l2(flush))
+    dlaunches = binding.launch_count() - dl0
+    dms = dms_total / args.decode_steps
+    dec_value = dw.n_all * 32768 / (dms * 1e-3)
+    for i in range(2):
+        dw.step(i, True)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for i in range(args.decode_steps):
+        dw.step(i, True)
+    barrier_sync(world)
+    de2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.decode_steps
+    dec_e2e = dw.n_all * 32768 / (de2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    peaks = ffma_peak(binding)
+    peak = min(FP32_PEAK_THEORETICAL, max(peaks.values()))
+    cs = args.chanstr
+    t_ach = train_value / world * F_TRAIN[cs] / 1e12
+    d_ach = dec_value / world / 32768 * F_DEC[cs] / 1e12
+    line = dict(
+        metric="train_blocks_per_sec", value=train_value, unit="blocks/s", n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32", data="synthetic", config=workload_config(args, world), clocks=clocks,
+        e2e=dict(value=train_e2e, unit="blocks/s", h2d_bytes_per_step=TrainWorkload.h2d_bytes,
+                 d2h_bytes_per_step=TrainWorkload.d2h_bytes),
+        gpu_launches=int(launches),
+        roofline=dict(bound="fp32", achieved=t_ach, peak=peak, unit="TFLOP/s", frac=t_ach / peak, traffic=None,
+                      per_gpu=True, algorithmic_flop_per_block=F_TRAIN[cs],
+                      peak_source="live nvf_ffma_microbench (MEASURED_PEAKS.json has no fp32 figure): "
+                                  "ffma %.1f, ffma2 %.1f TFLOP/s; theoretical 74.4 at 1965 MHz; denominator = min"
+                                  % (peaks["ffma"], peaks["ffma2"]),
+                      kernel="whole train step (layer-wise kernels)"),
+        decode=dict(metric="decoded_voxels_per_sec", value=dec_value, unit="voxels/s", ms_per_step=dms,
+                    blocks=dw.n_all, points=int(dw.points), gpu_launches=int(dlaunches), steps=args.decode_steps,
+                    workload="decode of all %d synthetic vox%d leaf blocks, thh %.2f, chanstr %s, calibrated ~2.1%% occupancy"
+                             % (dw.n_all, 10 if args.resolution == 1024 else 11, HP["thh"], cs),
+                    e2e=dict(value=dec_e2e, unit="voxels/s",
+                             h2d_bytes_per_step=int(dw.n_all * (96 + 12)), d2h_bytes_per_step=int(dw.points * 12)),
+                    roofline=dict(bound="fp32", achieved=d_ach, peak=peak, unit="TFLOP/s", frac=d_ach / peak,
+                                  traffic=None, per_gpu=True, algorithmic_flop_per_block=F_DEC[cs],
+                                  kernel="k_decode_fused_A" if cs == "8,16,8,8" else "layer-wise kernels")),
+    )
+    if not args.skip_cpu_baseline and world == 1:
+        line["cpu_baseline"], _ = cpu_train_baseline(args, pts, origins, budget_s=15.0)
+        line["decode"]["cpu_baseline"] = cpu_decode_baseline(args, origins, budget_s=10.0)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,8 @@ int nvf_abi_version(void);
 const char* nvf_strerror(int code);
 /* cudaError_t of the last failing CUDA call on this thread (0 if none). */
 int nvf_last_cuda_error(void);
+/* number of CUDA kernels this library has launched so far in this process. */
+long long nvf_launch_count(void);
 /* 1 if a fused (single-kernel, activations on chip) decode kernel exists for desc. */
 int nvf_has_fused_decode(const NvfDesc* desc);
 

@@ -28,7 +28,7 @@ NVF_MODE_DECODE, NVF_MODE_TRAIN = 0, 1
 NVF_BWD_WGRAD, NVF_BWD_DLATENT = 1, 2
 NVF_LOSS_SUMS = 20
 EXPORTS = (
-    "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_has_fused_decode", "nvf_workspace_bytes",
+    "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_launch_count", "nvf_has_fused_decode", "nvf_workspace_bytes",
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
     "nvf_ffma_microbench",
 )
@@ -79,6 +79,7 @@ class Binding:
         L.nvf_strerror.restype = C.c_char_p
         L.nvf_strerror.argtypes = [C.c_int]
         L.nvf_last_cuda_error.restype = C.c_int
+        L.nvf_launch_count.restype = C.c_longlong
         L.nvf_has_fused_decode.argtypes = [C.POINTER(NvfDesc)]
         L.nvf_workspace_bytes.argtypes = [C.POINTER(NvfDesc), C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
         vp = C.c_void_p
@@ -231,6 +232,9 @@ class Binding:
                                      _ptr(g[1]), _ptr(g[2]), _ptr(ws), ws.numel(), self._stream(dev))
         self.check(rc, "nvf_loss_seeds")
         return sums, g
+
+    def launch_count(self) -> int:
+        return int(self.lib.nvf_launch_count())
 
     def ffma_microbench(self, variant: int, iters: int, sink: torch.Tensor) -> float:
         flops = C.c_double(0)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 
 #include "nvf_api_impl.h"
 
@@ -11,6 +12,7 @@ using namespace nvf;
 namespace {
 
 thread_local int g_last_cuda = 0;
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
 
 template <class TS>
 struct DevEnv {
@@ -159,7 +161,10 @@ struct DevLauncher {
     }
     return true;
   }
-  void post() { chk(cudaGetLastError()); }
+  void post() {
+    chk(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   int sms() const { return n_sms; }
   int error() const { return rc; }
 
@@ -223,6 +228,8 @@ const char* nvf_strerror(int code) {
 }
 
 int nvf_last_cuda_error(void) { return g_last_cuda; }
+
+long long nvf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nvf_has_fused_decode(const NvfDesc* desc) { return desc && is_cfg_A(*desc) ? 1 : 0; }
 

@@ -1,0 +1,121 @@
+"""Public ops of the B200 NVF path (PyTorch-facing side of the C ABI).
+
+* `decode_blocks`   - batched replacement of the per-block loop in decode()/encode()
+                      (NVFPCC.py:625-638, :505-539): latents -> ordered points.
+* `nvf_decoder`     - differentiable CompDecoder.forward on effective tensors
+                      (utils/network.py:4758-4768) -> (out, cls1, cls0).
+* `rd_distortion`   - differentiable fused distortion losses + metrics
+                      (utils/loss.py:61-121, NVFPCC.py:76-88,166-184).
+
+All ops run hand-written sm_100a kernels through `libnvf_b200.so`; there is no
+CPU implementation and no fallback: without a CUDA device they raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import WEIGHT_FIELDS, NvfError
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise NvfError("nvfpcc_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev(t: Optional[torch.Tensor], dev: torch.device, dtype=None):
+    if t is None:
+        return None
+    return t.to(device=dev, dtype=dtype if dtype is not None else t.dtype, non_blocking=True)
+
+
+def decode_blocks(ch: int, channels: Sequence[int], weights: Dict[str, torch.Tensor], latents: torch.Tensor,
+                  origins: Optional[torch.Tensor], thh: float, return_prob: bool = False,
+                  return_host: Optional[bool] = None):
+    """latents [N,ch,2,2,2] (rounded), origins [N,3] -> dict(coords int32 [K,3], counts int32 [N], prob?).
+
+    Inputs may live on the host (ideally pinned) or on the device; host inputs are
+    copied in and, unless `return_host=False`, results are copied back.  Point
+    order: block order, then row-major (i,j,k), as NVFPCC.py:631-638 emits."""
+    dev = _device()
+    b = _lib.cuda_binding()
+    host_in = latents.device.type != "cuda"
+    if return_host is None:
+        return_host = host_in
+    w = {k: _to_dev(v, dev, torch.float32) for k, v in weights.items()}
+    r = b.decode(b.desc(ch, channels), w, _to_dev(latents, dev, torch.float32),
+                 _to_dev(origins, dev, torch.int32), thh, want_prob=return_prob)
+    out = dict(coords=r["coords"], counts=r["counts"], prob=r["prob"], mask=r["mask"])
+    if return_host:
+        out = {k: (None if v is None else v.cpu()) for k, v in out.items()}
+    return out
+
+
+class _NvfDecoderFn(torch.autograd.Function):
+    """forward: nvf_train_forward; backward: nvf_train_backward.  Inputs: latent, then the 20
+    effective tensors in WEIGHT_FIELDS order (plus two python flags)."""
+
+    @staticmethod
+    def forward(ctx, ch, channels, latent, *ws):
+        b = _lib.cuda_binding()
+        if latent.device.type != "cuda":
+            raise NvfError("nvf_decoder needs CUDA tensors; there is no CPU fallback")
+        weights = dict(zip(WEIGHT_FIELDS, ws))
+        desc = b.desc(ch, channels)
+        out, cls1, cls0, wsbuf, _ = b.train_forward(desc, weights, latent)
+        ctx.desc_args = (ch, tuple(channels))
+        ctx.wsbuf = wsbuf
+        ctx.save_for_backward(latent, *ws)
+        return out, cls1, cls0
+
+    @staticmethod
+    def backward(ctx, g_out, g_cls1, g_cls0):
+        b = _lib.cuda_binding()
+        latent, *ws = ctx.saved_tensors
+        weights = dict(zip(WEIGHT_FIELDS, ws))
+        need_lat = ctx.needs_input_grad[2]
+        need_w = any(ctx.needs_input_grad[3:])
+        ch, channels = ctx.desc_args
+        g_lat, grads = b.train_backward(b.desc(ch, channels), weights, latent, ctx.wsbuf, g_out, g_cls1, g_cls0,
+                                        need_w, need_lat)
+        ctx.wsbuf = None
+        gw = tuple(grads.get(k) if ctx.needs_input_grad[3 + i] else None for i, k in enumerate(WEIGHT_FIELDS))
+        return (None, None, g_lat) + gw
+
+
+def nvf_decoder(ch: int, channels: Sequence[int], latent: torch.Tensor, weights: Dict[str, torch.Tensor]):
+    """Differentiable decoder on effective tensors -> (out [N,1,32^3], cls1 [N,1,16^3], cls0 [N,1,8^3])."""
+    return _NvfDecoderFn.apply(int(ch), tuple(int(c) for c in channels), latent, *[weights[k] for k in WEIGHT_FIELDS])
+
+
+class _RdDistortionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, cls1, cls0, gt, dist, alpha_main, alpha_aux, thh_metric):
+        b = _lib.cuda_binding()
+        if out.device.type != "cuda":
+            raise NvfError("rd_distortion needs CUDA tensors; there is no CPU fallback")
+        need = any(t.requires_grad for t in (out, cls1, cls0))
+        sums, seeds = b.loss_seeds(out, cls1, cls0, gt, dist, alpha_main, alpha_aux, thh_metric, want_seeds=need)
+        ctx.save_for_backward(*[s for s in seeds if s is not None])
+        ctx.have = need
+        ctx.mark_non_differentiable(sums)
+        f = sums[:3].to(torch.float32)
+        return f[0], f[1], f[2], sums
+
+    @staticmethod
+    def backward(ctx, g_bce, g_ms0, g_ms1, _g_sums):
+        if not ctx.have:
+            return (None,) * 8
+        s_out, s_cls1, s_cls0 = ctx.saved_tensors
+        return s_out * g_bce, s_cls1 * g_ms1, s_cls0 * g_ms0, None, None, None, None, None
+
+
+def rd_distortion(out, cls1, cls0, gt, dist, alpha_main: float = 0.9, alpha_aux: float = 0.85,
+                  thh_metric: float = 0.6):
+    """-> (bce, ms0, ms1, sums[20] float64).  bce = get_surf_focal_dense(out, gt, dist, beta=1, alpha_main);
+    ms0/ms1 = get_focal_dense on the 8^3 / 16^3 heads against max-pooled GT (NVFPCC.py:166-184);
+    sums: see include/nvf_b200.h (sse/denom at thh_metric, tp/ap/tn/an of each head at 0.5)."""
+    return _RdDistortionFn.apply(out, cls1, cls0, gt, dist, float(alpha_main), float(alpha_aux), float(thh_metric))

@@ -105,6 +105,7 @@ extern "C" {
 int nvf_abi_version(void) { return NVF_ABI_VERSION; }
 const char* nvf_strerror(int code) { return code == NVF_OK ? "ok" : "error (emulator)"; }
 int nvf_last_cuda_error(void) { return 0; }
+long long nvf_launch_count(void) { return 0; }
 int nvf_has_fused_decode(const NvfDesc* desc) { return desc && is_cfg_A(*desc) ? 1 : 0; }
 
 int nvf_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, int mode, size_t* bytes_out) {
