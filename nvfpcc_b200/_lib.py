@@ -27,6 +27,7 @@ WEIGHT_FIELDS = (
 NVF_MODE_DECODE, NVF_MODE_TRAIN = 0, 1
 NVF_BWD_WGRAD, NVF_BWD_DLATENT = 1, 2
 NVF_LOSS_SUMS = 20
+NVF_LOSS_CHUNKS = 8   # CTAs per block of nvf_loss_seeds (workspace: 8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1) bytes)
 EXPORTS = (
     "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_launch_count", "nvf_has_fused_decode", "nvf_workspace_bytes",
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
@@ -225,7 +226,7 @@ class Binding:
         n = int(out.shape[0])
         ts = [t.detach().contiguous().float() for t in (out, cls1, cls0, gt, dist)]
         sums = torch.zeros((NVF_LOSS_SUMS,), dtype=torch.float64, device=dev)
-        ws = self.cached_workspace(8 * NVF_LOSS_SUMS * (n + 1), dev, "loss")
+        ws = self.cached_workspace(8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1), dev, "loss")
         g = [torch.empty_like(t) for t in ts[:3]] if want_seeds else [None, None, None]
         rc = self.lib.nvf_loss_seeds(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), n,
                                      float(alpha_main), float(alpha_aux), float(thh_metric), _ptr(sums), _ptr(g[0]),

@@ -16,6 +16,18 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 inline bool is_cfg_A(const NvfDesc& d) { return d.ch == 3 && d.c0 == 8 && d.c1 == 16 && d.c2 == 8 && d.c3 == 8; }
 constexpr int64_t kGenericDecodeChunk = 128;  // blocks per pass of the layer-wise decode path
+constexpr int kMaxPartialCtas = 304;          // persistent CTAs of a split-K weight-gradient kernel (2 per SM)
+// scratch for the split-K partial results of one backward pass: every weight-gradient kernel
+// writes <= kMaxPartialCtas partial copies of its layer's gradient; per-block partials of the
+// stem / bias sums need n-proportional room.
+inline size_t partial_floats(const NvfDesc& d, int64_t n) {
+  const size_t params = (size_t)d.ch * d.c0 * 125 + (size_t)d.c0 * d.c1 * 125 + (size_t)d.c1 * d.c2 * 125 +
+                        (size_t)d.c2 * d.c3 * 125 + (size_t)d.c2 * d.c2 * 64 + (size_t)d.c3 * d.c3 * 64 +
+                        27 * (size_t)(d.c1 + d.c2 + d.c3) + 2 * (size_t)(d.c0 + d.c1 + d.c2 + d.c3) + 64 * 24;
+  const size_t stem = (size_t)d.c0 * d.c1 * 125 + d.c1 + (size_t)d.c0 * d.c0 + d.c0 + (size_t)d.ch * d.c0 * 125 + d.c0;
+  return (size_t)kMaxPartialCtas * params +
+         (size_t)n * (stem + (size_t)d.c0 * d.c0 + 8 * (size_t)(d.c0 + d.c1 + d.c2 + d.c3) + 64 * 16);
+}
 
 struct DecodeWs {
   size_t off_packed, off_scratch, off_mask, off_offsets, total;
@@ -41,7 +53,7 @@ struct DecodeWs {
 };
 
 struct TrainWs {
-  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_loss, total;
+  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_p2, off_p1, off_p0, off_loss, off_partial, total;
   static TrainWs make(const NvfDesc& d, int64_t n) {
     TrainWs L{};
     const Stash s = Stash::make(d);
@@ -55,7 +67,11 @@ struct TrainWs {
     L.off_gl2 = take(sizeof(float) * (size_t)kVox * n);
     L.off_gl1 = take(sizeof(float) * (size_t)4096 * n);
     L.off_gl0 = take(sizeof(float) * (size_t)512 * n);
-    L.off_loss = take(sizeof(double) * (size_t)NVF_LOSS_SUMS * (n + 1));
+    L.off_p2 = take(sizeof(float) * (size_t)kVox * n);   // probabilities of the three heads (forward -> backward)
+    L.off_p1 = take(sizeof(float) * (size_t)4096 * n);
+    L.off_p0 = take(sizeof(float) * (size_t)512 * n);
+    L.off_loss = take(sizeof(double) * (size_t)NVF_LOSS_SUMS * (n * kLossChunks + 1));
+    L.off_partial = take(sizeof(float) * partial_floats(d, n));
     L.total = o;
     return L;
   }
@@ -64,10 +80,20 @@ struct TrainWs {
 template <class L>
 struct Api {
   static void layer(L& l, const LayerParams& p) {
-    if (p.CO == 1) l.template layer<1>(p);
-    else if (p.CO % 16 == 0) l.template layer<16>(p);
-    else if (p.CO % 8 == 0) l.template layer<8>(p);
+    if (l.fast_layer(p)) return;
+    // generic kernel: the per-thread channel tile shrinks when the layer is too small to fill the GPU
+    const int64_t pos = (int64_t)p.n * p.Dout * p.Dout * ((p.Dout + 3) / 4);
+    const int64_t want = (int64_t)l.sms() * 2 * kThreads;
+    if (p.CO % 16 == 0 && pos * (p.CO / 16) >= want) l.template layer<16>(p);
+    else if (p.CO % 8 == 0 && pos * (p.CO / 8) >= want) l.template layer<8>(p);
+    else if (p.CO % 4 == 0) l.template layer<4>(p);
     else l.template layer<1>(p);
+  }
+  // weight gradient + bias gradient (db = per-channel sum of the output gradient `c.g`)
+  static void wgrad_bias(L& l, const WgradParams& p, const ChanSumParams& c) {
+    if (l.fast_wgrad(p, c)) return;
+    wgrad(l, p);
+    l.chansum(c, c.C);
   }
   static void wgrad(L& l, const WgradParams& p) {
     const bool c8 = p.CA % 8 == 0;
@@ -112,8 +138,10 @@ struct Api {
   }
 
   // Layer-wise forward over `n` blocks.  stash: n * Stash::per_block floats.
+  // p2/p1/p0: optional second copies of the three heads' probabilities (kept for the backward pass)
   static void forward_layers(L& l, const NvfDesc& d, const NvfWeights& w, const float* packed, const float* latent,
-                             int n, float* stash, float* out, float* cls1, float* cls0) {
+                             int n, float* stash, float* out, float* cls1, float* cls0, float* p2 = nullptr,
+                             float* p1 = nullptr, float* p0 = nullptr) {
     const Stash s = Stash::make(d);
     const GenericPacked g = GenericPacked::make(d);
     // NOTE: the stash is laid out tensor-major ([tensor][n][...]) so that every layer sees a dense batch.
@@ -122,17 +150,20 @@ struct Api {
     float* a5 = stash + s.a5 * n;
     LayerParams p{};
     p.n = n;
-    // up0: convT k5 s2 p2 op1 (utils/network.py:4671-4680)
-    p = LayerParams{latent, x0, packed + g.up0, w.up0_b, nullptr, nullptr, n, d.ch, d.c0, 2, 2, 4, 4, 2, ACT_NONE, OP_CONVT};
-    layer(l, p);
-    IgdnParams ip{x0, a0, nullptr, w.igdn_beta, w.igdn_gamma, nullptr, nullptr, n, d.c0};
-    l.template generic<IgdnFwdKernel>(ip, (int)((int64_t)n * d.c0 * 64 + kThreads - 1) / kThreads);
-    // conv0: convT k5 s2 p2 op1 + ReLU (:4682-4691, :4760)
-    p = LayerParams{a0, a1, packed + g.conv0, w.conv0_b, nullptr, nullptr, n, d.c0, d.c1, 4, 4, 8, 8, 2, ACT_RELU, OP_CONVT};
-    layer(l, p);
-    if (cls0) {  // conv0_cls + sigmoid (:4743-4751, :4761)
-      p = LayerParams{a1, cls0, packed + g.cls0, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
+    if (!l.fast_stem_fwd(d, w, packed + g.up0, packed + g.conv0, packed + g.cls0, latent, n, x0, a0, a1, cls0, p0)) {
+      // up0: convT k5 s2 p2 op1 (utils/network.py:4671-4680)
+      p = LayerParams{latent, x0, packed + g.up0, w.up0_b, nullptr, nullptr, n, d.ch, d.c0, 2, 2, 4, 4, 2, ACT_NONE, OP_CONVT};
       layer(l, p);
+      IgdnParams ip{x0, a0, nullptr, w.igdn_beta, w.igdn_gamma, nullptr, nullptr, n, d.c0};
+      l.template generic<IgdnFwdKernel>(ip, (int)((int64_t)n * d.c0 * 64 + kThreads - 1) / kThreads);
+      // conv0: convT k5 s2 p2 op1 + ReLU (:4682-4691, :4760)
+      p = LayerParams{a0, a1, packed + g.conv0, w.conv0_b, nullptr, nullptr, n, d.c0, d.c1, 4, 4, 8, 8, 2, ACT_RELU, OP_CONVT};
+      layer(l, p);
+      if (cls0) {  // conv0_cls + sigmoid (:4743-4751, :4761)
+        p = LayerParams{a1, cls0, packed + g.cls0, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
+        p.out2 = p0;
+        layer(l, p);
+      }
     }
     // up1: convT k5 s2 p0 + ReLU (:4693-4700, :4762)
     p = LayerParams{a1, a2, packed + g.up1, w.up1_b, nullptr, nullptr, n, d.c1, d.c2, 8, 8, 19, 20, 0, ACT_RELU, OP_CONVT};
@@ -142,6 +173,7 @@ struct Api {
     layer(l, p);
     if (cls1) {  // conv1_cls + sigmoid (:4733-4741, :4764)
       p = LayerParams{a3, cls1, packed + g.cls1, w.cls1_b, nullptr, nullptr, n, d.c2, 1, 16, 16, 16, 16, 1, ACT_SIGMOID, OP_CORR3};
+      p.out2 = p1;
       layer(l, p);
     }
     // up2: convT k5 s2 p0 + ReLU (:4712-4719, :4765)
@@ -152,6 +184,7 @@ struct Api {
     layer(l, p);
     // conv2_cls + sigmoid (:4731, :4767-4768)
     p = LayerParams{a5, out, packed + g.cls2, w.cls2_b, nullptr, nullptr, n, d.c3, 1, 32, 32, 32, 32, 1, ACT_SIGMOID, OP_CORR3};
+    p.out2 = p2;
     layer(l, p);
   }
 
@@ -252,7 +285,8 @@ struct Api {
     char* ws = (char*)workspace;
     float* packed = (float*)(ws + W.off_packed);
     pack_all(l, *desc, *w, packed, true, true);
-    forward_layers(l, *desc, *w, packed, latent, (int)n, (float*)(ws + W.off_stash), out, cls1, cls0);
+    forward_layers(l, *desc, *w, packed, latent, (int)n, (float*)(ws + W.off_stash), out, cls1, cls0,
+                   (float*)(ws + W.off_p2), (float*)(ws + W.off_p1), (float*)(ws + W.off_p0));
     return l.error();
   }
 
@@ -261,11 +295,11 @@ struct Api {
                         double* sums_out, float* g_out, float* g_cls1, float* g_cls0, void* workspace,
                         size_t workspace_bytes) {
     if (!out || !cls1 || !cls0 || !gt || !dist || !sums_out || !workspace || n <= 0) return NVF_ERR_INVALID_ARG;
-    if (workspace_bytes < sizeof(double) * NVF_LOSS_SUMS * (size_t)n) return NVF_ERR_WORKSPACE;
+    if (workspace_bytes < sizeof(double) * NVF_LOSS_SUMS * (size_t)n * kLossChunks) return NVF_ERR_WORKSPACE;
     LossParams lp{out, cls1, cls0, gt, dist, g_out, g_cls1, g_cls0, (double*)workspace, alpha_main, alpha_aux,
                   thh_metric, (int32_t)n};
-    l.loss(lp, (int)n);
-    LossFinalKernel::Params fp{(const double*)workspace, sums_out, (int32_t)n};
+    l.loss(lp, (int)n * kLossChunks);
+    LossFinalKernel::Params fp{(const double*)workspace, sums_out, (int32_t)n * kLossChunks};
     l.template generic<LossFinalKernel>(fp, 1);
     return l.error();
   }
@@ -296,55 +330,44 @@ struct Api {
     float* gl2 = (float*)(ws + W.off_gl2);
     float* gl1 = (float*)(ws + W.off_gl1);
     float* gl0 = (float*)(ws + W.off_gl0);
+    l.set_partial((float*)(ws + W.off_partial), partial_floats(d, n));
     const bool wg = (flags & NVF_BWD_WGRAD) != 0;
-    // the heads' probabilities are not stashed: recompute p from the stash is avoided by requiring the caller to
-    // pass dL/dp seeds already multiplied?  No: p = sigmoid(logit) is needed; it is recomputed here from a5/a3/a1.
-    // (cheap: 3 % of the forward MACs) -> logits buffers gl* first hold p, then g_logit in place.
+    // the heads' probabilities were kept by nvf_train_forward: dL/dlogit = dL/dp * p (1 - p)
     LayerParams p{};
-    p = LayerParams{a5, gl2, packed + g.cls2, w->cls2_b, nullptr, nullptr, n, d.c3, 1, 32, 32, 32, 32, 1, ACT_SIGMOID, OP_CORR3};
-    layer(l, p);
-    p = LayerParams{a3, gl1, packed + g.cls1, w->cls1_b, nullptr, nullptr, n, d.c2, 1, 16, 16, 16, 16, 1, ACT_SIGMOID, OP_CORR3};
-    layer(l, p);
-    p = LayerParams{a1, gl0, packed + g.cls0, w->cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
-    layer(l, p);
-    auto sig = [&](const float* gp, float* buf, int64_t cnt) {
-      SigBwdParams sp{gp, buf, buf, cnt};
+    auto sig = [&](const float* gp, const float* prob, float* buf, int64_t cnt) {
+      SigBwdParams sp{gp, prob, buf, cnt};
       int grid = (int)((cnt + kThreads - 1) / kThreads);
       if (grid > 4096) grid = 4096;
       l.template generic<SigBwdKernel>(sp, grid);
     };
-    sig(g_out, gl2, (int64_t)n * kVox);
-    sig(g_cls1, gl1, (int64_t)n * 4096);
-    sig(g_cls0, gl0, (int64_t)n * 512);
+    sig(g_out, (const float*)(ws + W.off_p2), gl2, (int64_t)n * kVox);
+    sig(g_cls1, (const float*)(ws + W.off_p1), gl1, (int64_t)n * 4096);
+    sig(g_cls0, (const float*)(ws + W.off_p0), gl0, (int64_t)n * 512);
 
     // ---- conv2_cls ----
     if (wg) {
       WgradParams q{gl2, a5, gw->cls2_w, n, 1, d.c3, 32, 32, 32, 32, 3, 1, 1};
-      wgrad(l, q);
       ChanSumParams c{gl2, gw->cls2_b, n, 1, 32, 32};
-      l.chansum(c, 1);
+      wgrad_bias(l, q, c);
     }
     p = LayerParams{gl2, g5, packed + g.d_cls2, nullptr, nullptr, a5, n, 1, d.c3, 32, 32, 32, 32, 1, ACT_NONE, OP_CORR3};
     layer(l, p);
     // ---- conv2 ----
     if (wg) {
       WgradParams q{g5, a4, gw->conv2_w, n, d.c3, d.c3, 32, 32, 35, 36, 4, 1, 0};
-      wgrad(l, q);
       ChanSumParams c{g5, gw->conv2_b, n, d.c3, 32, 32};
-      l.chansum(c, d.c3);
+      wgrad_bias(l, q, c);
     }
     p = LayerParams{g5, g4, packed + g.d_conv2, nullptr, nullptr, a4, n, d.c3, d.c3, 32, 32, 35, 36, 3, ACT_NONE, OP_CORR4};
     layer(l, p);
     // ---- up2 (+ conv1_cls branch) ----
     if (wg) {
       WgradParams q{a3, g4, gw->up2_w, n, d.c2, d.c3, 16, 16, 35, 36, 5, 2, 0};
-      wgrad(l, q);
       ChanSumParams c{g4, gw->up2_b, n, d.c3, 35, 36};
-      l.chansum(c, d.c3);
+      wgrad_bias(l, q, c);
       WgradParams q1{gl1, a3, gw->cls1_w, n, 1, d.c2, 16, 16, 16, 16, 3, 1, 1};
-      wgrad(l, q1);
       ChanSumParams c1{gl1, gw->cls1_b, n, 1, 16, 16};
-      l.chansum(c1, 1);
+      wgrad_bias(l, q1, c1);
     }
     p = LayerParams{gl1, tmp3, packed + g.d_cls1, nullptr, nullptr, nullptr, n, 1, d.c2, 16, 16, 16, 16, 1, ACT_NONE, OP_CORR3};
     layer(l, p);
@@ -353,54 +376,52 @@ struct Api {
     // ---- conv1 ----
     if (wg) {
       WgradParams q{g3, a2, gw->conv1_w, n, d.c2, d.c2, 16, 16, 19, 20, 4, 1, 0};
-      wgrad(l, q);
       ChanSumParams c{g3, gw->conv1_b, n, d.c2, 16, 16};
-      l.chansum(c, d.c2);
+      wgrad_bias(l, q, c);
     }
     p = LayerParams{g3, g2, packed + g.d_conv1, nullptr, nullptr, a2, n, d.c2, d.c2, 16, 16, 19, 20, 3, ACT_NONE, OP_CORR4};
     layer(l, p);
     // ---- up1 (+ conv0_cls branch) ----
     if (wg) {
       WgradParams q{a1, g2, gw->up1_w, n, d.c1, d.c2, 8, 8, 19, 20, 5, 2, 0};
-      wgrad(l, q);
       ChanSumParams c{g2, gw->up1_b, n, d.c2, 19, 20};
-      l.chansum(c, d.c2);
+      wgrad_bias(l, q, c);
       WgradParams q0{gl0, a1, gw->cls0_w, n, 1, d.c1, 8, 8, 8, 8, 3, 1, 1};
-      wgrad(l, q0);
       ChanSumParams c0{gl0, gw->cls0_b, n, 1, 8, 8};
-      l.chansum(c0, 1);
+      wgrad_bias(l, q0, c0);
     }
     p = LayerParams{gl0, tmp1, packed + g.d_cls0, nullptr, nullptr, nullptr, n, 1, d.c1, 8, 8, 8, 8, 1, ACT_NONE, OP_CORR3};
     layer(l, p);
     p = LayerParams{g2, g1, packed + g.d_up1, nullptr, tmp1, a1, n, d.c2, d.c1, 19, 20, 8, 8, 0, ACT_NONE, OP_CORR_S2};
     layer(l, p);
-    // ---- conv0 ----
-    if (wg) {
-      WgradParams q{a0, g1, gw->conv0_w, n, d.c0, d.c1, 4, 4, 8, 8, 5, 2, 2};
-      wgrad(l, q);
-      ChanSumParams c{g1, gw->conv0_b, n, d.c1, 8, 8};
-      l.chansum(c, d.c1);
-    }
-    p = LayerParams{g1, gy0, packed + g.d_conv0, nullptr, nullptr, nullptr, n, d.c1, d.c0, 8, 8, 4, 4, 2, ACT_NONE, OP_CORR_S2};
-    layer(l, p);
-    // ---- IGDN ----
-    {
-      IgdnParams ip{x0, gx0, gy0, w->igdn_beta, w->igdn_gamma, wg ? gw->igdn_beta : nullptr,
-                    wg ? gw->igdn_gamma : nullptr, n, d.c0};
-      l.template generic<IgdnBwdDxKernel>(ip, (int)(((int64_t)n * d.c0 * 64 + kThreads - 1) / kThreads));
-      if (wg) l.template generic<IgdnBwdParamKernel>(ip, 1);
-    }
-    // ---- up0 ----
-    if (wg) {
-      WgradParams q{latent, gx0, gw->up0_w, n, d.ch, d.c0, 2, 2, 4, 4, 5, 2, 2};
-      wgrad(l, q);
-      ChanSumParams c{gx0, gw->up0_b, n, d.c0, 4, 4};
-      l.chansum(c, d.c0);
-    }
-    if (flags & NVF_BWD_DLATENT) {
-      p = LayerParams{gx0, g_latent, packed + g.d_up0, nullptr, nullptr, nullptr, n, d.c0, d.ch, 4, 4, 2, 2, 2, ACT_NONE, OP_CORR_S2};
+    if (!l.fast_stem_bwd(d, *w, latent, n, x0, a0, g1, wg ? gw : nullptr, (flags & NVF_BWD_DLATENT) ? g_latent : nullptr)) {
+      // ---- conv0 ----
+      if (wg) {
+        WgradParams q{a0, g1, gw->conv0_w, n, d.c0, d.c1, 4, 4, 8, 8, 5, 2, 2};
+        ChanSumParams c{g1, gw->conv0_b, n, d.c1, 8, 8};
+        wgrad_bias(l, q, c);
+      }
+      p = LayerParams{g1, gy0, packed + g.d_conv0, nullptr, nullptr, nullptr, n, d.c1, d.c0, 8, 8, 4, 4, 2, ACT_NONE, OP_CORR_S2};
       layer(l, p);
+      // ---- IGDN ----
+      {
+        IgdnParams ip{x0, gx0, gy0, w->igdn_beta, w->igdn_gamma, wg ? gw->igdn_beta : nullptr,
+                      wg ? gw->igdn_gamma : nullptr, n, d.c0};
+        l.template generic<IgdnBwdDxKernel>(ip, (int)(((int64_t)n * d.c0 * 64 + kThreads - 1) / kThreads));
+        if (wg && !l.fast_igdn_param(ip)) l.template generic<IgdnBwdParamKernel>(ip, 1);
+      }
+      // ---- up0 ----
+      if (wg) {
+        WgradParams q{latent, gx0, gw->up0_w, n, d.ch, d.c0, 2, 2, 4, 4, 5, 2, 2};
+        ChanSumParams c{gx0, gw->up0_b, n, d.c0, 4, 4};
+        wgrad_bias(l, q, c);
+      }
+      if (flags & NVF_BWD_DLATENT) {
+        p = LayerParams{gx0, g_latent, packed + g.d_up0, nullptr, nullptr, nullptr, n, d.c0, d.ch, 4, 4, 2, 2, 2, ACT_NONE, OP_CORR_S2};
+        layer(l, p);
+      }
     }
+    l.flush_reduce();
     return l.error();
   }
 };

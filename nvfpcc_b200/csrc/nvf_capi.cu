@@ -6,6 +6,10 @@
 #include <atomic>
 
 #include "nvf_api_impl.h"
+#include "nvf_fast_conv.cuh"
+#include "nvf_fast_convt.cuh"
+#include "nvf_fast_misc.cuh"
+#include "nvf_fast_stem.cuh"
 
 using namespace nvf;
 
@@ -206,6 +210,266 @@ struct DevLauncher {
   }
   void mask(const MaskParams& p, int grid) { k_mask<<<grid, kThreads, 0, st>>>(p); post(); }
   void loss(const LossParams& p, int grid) { k_loss<<<grid, kThreads, 0, st>>>(p); post(); }
+
+  // ---- shared-memory tiled kernels of the training path (nvf_fast_*.cuh) --------------------
+  float* part_base = nullptr;   // scratch for split-K partial results (bump allocated per call)
+  size_t part_off = 0, part_cap = 0;
+  fast::ReduceParams red{};     // pending fixed-order reductions, flushed by flush_reduce()
+
+  void set_partial(float* base, size_t floats) { part_base = base; part_cap = floats; part_off = 0; }
+  float* take_partial(size_t floats) {
+    floats = (floats + 63) / 64 * 64;
+    if (!part_base || part_off + floats > part_cap) return nullptr;
+    float* r = part_base + part_off;
+    part_off += floats;
+    return r;
+  }
+  void add_reduce(const fast::ReduceJob& j) {
+    if (red.njobs == fast::kMaxReduceJobs) flush_reduce();
+    red.job[red.njobs++] = j;
+  }
+  void flush_reduce() {
+    if (!red.njobs) return;
+    int nmax = 0;
+    for (int i = 0; i < red.njobs; ++i) nmax = red.job[i].n_w + red.job[i].n_b > nmax ? red.job[i].n_w + red.job[i].n_b : nmax;
+    int gx = (nmax + 31) / 32;
+    if (gx > 1024) gx = 1024;
+    fast::k_reduce_partials<<<dim3(gx, red.njobs), 256, 0, st>>>(red);
+    post();
+    red.njobs = 0;
+  }
+  template <class KernelT>
+  bool smem_attr(KernelT* k, int bytes) {
+    return chk(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
+
+  template <int K, int CI, int CO, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB>
+  bool conv_s1(const LayerParams& p) {
+    using G = fast::ConvS1Cfg<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC>;
+    static_assert(G::SMEM_BYTES <= 227 * 1024, "conv_s1 smem");
+    auto* k = fast::k_conv_s1<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, MINB>;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::ConvS1Params q{p.in, p.out, p.out2, p.Wp, p.bias, p.mask, p.n, p.act};
+    k<<<p.n * G::TILES_Z * G::TILES_Y, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    post();
+    return true;
+  }
+  template <int CI, int CO, int DIN, int MINB>
+  bool convT_fwd(const LayerParams& p) {
+    using G = fast::ConvTFwdCfg<CI, CO, DIN>;
+    static_assert(G::SMEM_BYTES <= 227 * 1024, "convT fwd smem");
+    auto* k = fast::k_convT5_fwd<CI, CO, DIN, MINB>;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::ConvTFwdParams q{p.in, p.out, p.Wp, p.bias, p.n};
+    k<<<p.n * G::DOUT, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    post();
+    return true;
+  }
+  template <int CG, int CX, int DIN, int TY, int CGC, int MINB>
+  bool convT_dgrad(const LayerParams& p) {
+    using G = fast::ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
+    static_assert(G::SMEM_BYTES <= 227 * 1024, "convT dgrad smem");
+    auto* k = fast::k_convT5_dgrad<CG, CX, DIN, TY, CGC, MINB>;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::ConvTDgradParams q{p.in, p.out, p.Wp, p.add, p.mask, p.n};
+    k<<<p.n * DIN * G::BANDS, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    post();
+    return true;
+  }
+  // returns true when a tiled kernel handled the layer
+  bool fast_layer(const LayerParams& p) {
+    if (p.n <= 0) return false;
+    if (p.op == OP_CORR4 && p.CI == p.CO && !p.add && !p.out2 && p.act != ACT_SIGMOID) {
+      const bool fwd = p.P == 0 && !p.mask, dg = p.P == 3;
+      if (p.CI == 8) {
+        if (fwd && p.Din == 35) return conv_s1<4, 8, 8, 35, 0, 8, 16, 2, 4, 2>(p);
+        if (dg && p.Din == 32) return conv_s1<4, 8, 8, 32, 3, 9, 12, 2, 4, 2>(p);
+        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 4, 4>(p);
+        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 4, 4>(p);
+      } else if (p.CI == 16) {
+        if (fwd && p.Din == 35) return conv_s1<4, 16, 16, 35, 0, 8, 16, 1, 4, 2>(p);
+        if (dg && p.Din == 32) return conv_s1<4, 16, 16, 32, 3, 9, 12, 1, 4, 2>(p);
+        if (fwd && p.Din == 19) return conv_s1<4, 16, 16, 19, 0, 4, 8, 2, 4, 2>(p);
+        if (dg && p.Din == 16) return conv_s1<4, 16, 16, 16, 3, 5, 10, 2, 4, 2>(p);
+      }
+      return false;
+    }
+    if (p.op == OP_CORR3 && p.P == 1 && !p.add) {
+      if (p.CI == 1 && !p.out2 && p.act == ACT_NONE) {           // classifier data gradient 1 -> C
+        if (p.CO == 8 && p.Din == 32) return conv_s1<3, 1, 8, 32, 1, 8, 16, 2, 1, 2>(p);
+        if (p.CO == 8 && p.Din == 16) return conv_s1<3, 1, 8, 16, 1, 4, 8, 2, 1, 4>(p);
+        if (p.CO == 16 && p.Din == 8) return conv_s1<3, 1, 16, 8, 1, 2, 8, 1, 1, 4>(p);
+        if (p.CO == 16 && p.Din == 32) return conv_s1<3, 1, 16, 32, 1, 8, 16, 1, 1, 2>(p);
+        if (p.CO == 16 && p.Din == 16) return conv_s1<3, 1, 16, 16, 1, 4, 8, 2, 1, 4>(p);
+        if (p.CO == 32 && p.Din == 8) return conv_s1<3, 1, 32, 8, 1, 2, 8, 1, 1, 4>(p);
+      } else if (p.CO == 1 && !p.mask) {                          // classifier forward C -> 1
+        if (p.CI == 8 && p.Din == 32) return conv_s1<3, 8, 1, 32, 1, 8, 16, 2, 4, 2>(p);
+        if (p.CI == 8 && p.Din == 16) return conv_s1<3, 8, 1, 16, 1, 4, 8, 2, 4, 4>(p);
+        if (p.CI == 16 && p.Din == 8) return conv_s1<3, 16, 1, 8, 1, 2, 8, 2, 8, 4>(p);
+        if (p.CI == 16 && p.Din == 32) return conv_s1<3, 16, 1, 32, 1, 8, 16, 2, 4, 2>(p);
+        if (p.CI == 16 && p.Din == 16) return conv_s1<3, 16, 1, 16, 1, 4, 8, 2, 4, 4>(p);
+        if (p.CI == 32 && p.Din == 8) return conv_s1<3, 32, 1, 8, 1, 2, 8, 2, 8, 4>(p);
+      }
+      return false;
+    }
+    if (p.op == OP_CONVT && p.P == 0 && p.act == ACT_RELU && !p.add && !p.mask && !p.out2) {
+      if (p.CI == 8 && p.CO == 8 && p.Din == 16) return convT_fwd<8, 8, 16, 2>(p);
+      if (p.CI == 16 && p.CO == 8 && p.Din == 8) return convT_fwd<16, 8, 8, 2>(p);
+      if (p.CI == 16 && p.CO == 16 && p.Din == 16) return convT_fwd<16, 16, 16, 1>(p);
+      if (p.CI == 32 && p.CO == 16 && p.Din == 8) return convT_fwd<32, 16, 8, 1>(p);
+      return false;
+    }
+    if (p.op == OP_CORR_S2 && p.P == 0 && p.act == ACT_NONE && !p.bias && !p.out2) {
+      if (p.CI == 8 && p.CO == 8 && p.Dout == 16) return convT_dgrad<8, 8, 16, 16, 2, 2>(p);
+      if (p.CI == 8 && p.CO == 16 && p.Dout == 8) return convT_dgrad<8, 16, 8, 8, 2, 2>(p);
+      if (p.CI == 16 && p.CO == 16 && p.Dout == 16) return convT_dgrad<16, 16, 16, 16, 2, 1>(p);
+      if (p.CI == 16 && p.CO == 32 && p.Dout == 8) return convT_dgrad<16, 32, 8, 8, 2, 1>(p);
+      return false;
+    }
+    return false;
+  }
+
+  template <int C, int DG, int TYG, int MINB>
+  bool wgrad4(const WgradParams& p, float* db) {
+    using G = fast::WgradS1Cfg<C, DG, TYG>;
+    auto* k = fast::k_wgrad4_s1<C, DG, TYG, MINB>;
+    const int items = p.n * DG * G::BANDS;
+    int grid = n_sms * MINB;
+    if (grid > items) grid = items;
+    float* partial = take_partial((size_t)grid * G::OUT_FLOATS);
+    if (!partial) return false;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::WgradS1Params q{p.A, p.Sft, partial, p.n};
+    k<<<grid, 256, G::SMEM_BYTES, st>>>(q);
+    post();
+    add_reduce(fast::ReduceJob{partial, p.dW, db, grid, G::OUT_FLOATS, G::NW, C, 0, 0});
+    return true;
+  }
+  bool chansum_fast(const ChanSumParams& c) {
+    if (c.pitch % 4) return false;
+    const int zch = c.D >= 16 ? 4 : 1;
+    float* partial = take_partial((size_t)c.n * zch * c.C);
+    if (!partial) return false;
+    fast::ChanSumFastParams q{c.g, partial, c.n, c.C, c.D, c.pitch, zch};
+    fast::k_chansum_fast<<<c.n * zch * c.C, 256, 0, st>>>(q);
+    post();
+    add_reduce(fast::ReduceJob{partial, c.out, nullptr, c.n * zch, c.C, c.C, 0, 0, 0});
+    return true;
+  }
+  template <int CI, int CO, int DIN, int TYB, int CIB, int MINB>
+  bool convT_wgrad(const WgradParams& p, const ChanSumParams& c) {
+    using G = fast::ConvTWgradCfg<CI, CO, DIN, TYB, CIB>;
+    static_assert(G::SMEM_BYTES <= 227 * 1024, "convT wgrad smem");
+    auto* k = fast::k_convT5_wgrad<CI, CO, DIN, TYB, CIB, MINB>;
+    const int items = p.n * DIN * G::BANDS;
+    int grid = (n_sms * MINB + G::GROUPS - 1) / G::GROUPS;
+    if (grid > items) grid = items;
+    if (grid * G::GROUPS > kMaxPartialCtas) grid = kMaxPartialCtas / G::GROUPS;
+    float* partial = take_partial((size_t)grid * G::GROUPS * G::OUT_FLOATS);
+    if (!partial) return false;
+    if (!chansum_fast(c)) return false;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::ConvTWgradParams q{p.A, p.Sft, partial, p.n};
+    k<<<dim3(grid, G::GROUPS), 224, G::SMEM_BYTES, st>>>(q);
+    post();
+    for (int grp = 0; grp < G::GROUPS; ++grp) {
+      const int cog = grp % (CO / 8), cig = grp / (CO / 8);
+      // partial rows [ci_local][co_local 8][125] -> dW[(cig*CIB + ci)][cog*8 + co][125]
+      add_reduce(fast::ReduceJob{partial + (size_t)grp * grid * G::OUT_FLOATS,
+                                 p.dW + ((size_t)cig * CIB * CO + cog * 8) * 125, nullptr, grid, G::OUT_FLOATS,
+                                 G::OUT_FLOATS, 0, 8 * 125, CO * 125});
+    }
+    return true;
+  }
+  template <int C, int D, int TYB>
+  bool cls_wgrad(const WgradParams& p, float* db) {
+    using G = fast::ClsWgradCfg<C, D, TYB>;
+    auto* k = fast::k_cls_wgrad<C, D, TYB>;
+    const int items = p.n * D * G::BANDS;
+    int grid = n_sms * 2;
+    if (grid > items) grid = items;
+    float* partial = take_partial((size_t)grid * G::OUT_FLOATS);
+    if (!partial) return false;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::ClsWgradParams q{p.A, p.Sft, partial, p.n};
+    k<<<grid, 256, G::SMEM_BYTES, st>>>(q);
+    post();
+    add_reduce(fast::ReduceJob{partial, p.dW, db, grid, G::OUT_FLOATS, G::NW, 1, 0, 0});
+    return true;
+  }
+  // weight + bias gradient of one layer; false = not handled (the generic kernels run instead)
+  bool fast_wgrad(const WgradParams& p, const ChanSumParams& c) {
+    if (p.n <= 0 || !c.out) return false;
+    if (p.K == 4 && p.S == 1 && p.CA == p.CS && p.P == 0) {
+      if (p.CA == 8 && p.Da == 32) return wgrad4<8, 32, 8, 2>(p, c.out);
+      if (p.CA == 8 && p.Da == 16) return wgrad4<8, 16, 8, 2>(p, c.out);
+      if (p.CA == 16 && p.Da == 32) return wgrad4<16, 32, 4, 2>(p, c.out);
+      if (p.CA == 16 && p.Da == 16) return wgrad4<16, 16, 4, 2>(p, c.out);
+      return false;
+    }
+    if (p.K == 5 && p.S == 2 && p.P == 0) {
+      if (p.CA == 8 && p.CS == 8 && p.Da == 16) return convT_wgrad<8, 8, 16, 4, 8, 3>(p, c);
+      if (p.CA == 16 && p.CS == 8 && p.Da == 8) return convT_wgrad<16, 8, 8, 4, 16, 2>(p, c);
+      if (p.CA == 16 && p.CS == 16 && p.Da == 16) return convT_wgrad<16, 16, 16, 4, 16, 2>(p, c);
+      if (p.CA == 32 && p.CS == 16 && p.Da == 8) return convT_wgrad<32, 16, 8, 4, 16, 2>(p, c);
+      return false;
+    }
+    if (p.K == 3 && p.S == 1 && p.P == 1 && p.CA == 1) {
+      if (p.CS == 8 && p.Da == 32) return cls_wgrad<8, 32, 8>(p, c.out);
+      if (p.CS == 8 && p.Da == 16) return cls_wgrad<8, 16, 8>(p, c.out);
+      if (p.CS == 16 && p.Da == 8) return cls_wgrad<16, 8, 8>(p, c.out);
+      if (p.CS == 16 && p.Da == 32) return cls_wgrad<16, 32, 8>(p, c.out);
+      if (p.CS == 16 && p.Da == 16) return cls_wgrad<16, 16, 8>(p, c.out);
+      return false;
+    }
+    return false;
+  }
+  // stem (everything at <= 8^3): one CTA per block, see nvf_fast_stem.cuh
+  bool fast_stem_fwd(const NvfDesc& d, const NvfWeights& w, const float* up0_wp, const float* conv0_wp,
+                     const float* cls0_wp, const float* latent, int n, float* x0, float* a0, float* a1, float* cls0,
+                     float* cls0_copy) {
+    if (n <= 0 || d.c1 % 8 || d.c0 > 32) return false;
+    const int smem = (d.ch * 8 + 2 * d.c0 * 64 + d.c1 * 512) * (int)sizeof(float);
+    if (!smem_attr(fast::k_stem_fwd, smem)) return true;
+    fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
+                          cls0 ? cls0_wp : nullptr, w.cls0_b, x0, a0, a1, cls0, cls0_copy, n, d.ch, d.c0, d.c1};
+    fast::k_stem_fwd<<<n, fast::kStemThreads, smem, st>>>(q);
+    post();
+    return true;
+  }
+  bool fast_stem_bwd(const NvfDesc& d, const NvfWeights& w, const float* latent, int n, const float* x0,
+                     const float* a0, const float* g1, const NvfWeightGrads* gw, float* g_latent) {
+    if (n <= 0 || d.c1 % 8 || d.c0 > 32) return false;
+    const int pf = fast::stem_partial_floats(d.ch, d.c0, d.c1);
+    float* partial = nullptr;
+    if (gw) {
+      partial = take_partial((size_t)n * pf);
+      if (!partial) return false;
+    }
+    const int smem = (d.c1 * 512 + 9 * d.c0 * 64 + d.ch * 8) * (int)sizeof(float);
+    if (!smem_attr(fast::k_stem_bwd, smem)) return true;
+    fast::StemBwdParams q{latent, x0, a0, g1, w.igdn_beta, w.igdn_gamma, w.conv0_w, w.up0_w, partial, g_latent,
+                          n, d.ch, d.c0, d.c1, gw ? 1 : 0};
+    fast::k_stem_bwd<<<n, fast::kStemThreads, smem, st>>>(q);
+    post();
+    if (gw) {
+      const int n0 = d.c0 * d.c1 * 125, ng = d.c0 * d.c0, nu = d.ch * d.c0 * 125;
+      add_reduce(fast::ReduceJob{partial, gw->conv0_w, gw->conv0_b, n, pf, n0, d.c1, 0, 0});
+      add_reduce(fast::ReduceJob{partial + n0 + d.c1, gw->igdn_gamma, gw->igdn_beta, n, pf, ng, d.c0, 0, 0});
+      add_reduce(fast::ReduceJob{partial + n0 + d.c1 + ng + d.c0, gw->up0_w, gw->up0_b, n, pf, nu, d.c0, 0, 0});
+    }
+    return true;
+  }
+  bool fast_igdn_param(const IgdnParams& ip) {
+    if (!ip.dbeta || !ip.dgamma || ip.C > 32) return false;
+    float* partial = take_partial((size_t)ip.n * (ip.C * ip.C + ip.C));
+    if (!partial) return false;
+    fast::IgdnParamParams q{ip.x, ip.g, ip.beta, ip.gamma, partial, ip.n, ip.C};
+    fast::k_igdn_param<<<ip.n, 256, ip.C * 64 * 2 * sizeof(float), st>>>(q);
+    post();
+    add_reduce(fast::ReduceJob{partial, ip.dgamma, ip.dbeta, ip.n, ip.C * ip.C + ip.C, ip.C * ip.C, ip.C, 0, 0});
+    return true;
+  }
 };
 
 }  // namespace

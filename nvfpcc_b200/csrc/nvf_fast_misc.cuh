@@ -1,0 +1,176 @@
+// Small-layer kernels of the training path: weight gradient of the three
+// 3x3x3 classifier heads (conv2_cls / conv1_cls / conv0_cls, utils/network.py:
+// 4731-4751) and the IGDN parameter gradients (gdn_3d.py:137-159 backward).
+#pragma once
+#include <cuda_runtime.h>
+#include "nvf_common.h"
+
+namespace nvf {
+namespace fast {
+
+// dW[ci][kz][ky][kx] = sum_{b,pos} gl[b][pos] * a[b][ci][pos + k - 1]   (zero padding 1)
+// db                 = sum gl
+// Thread = (ci, kz, ky) owns 3 outputs; NSET position sets share the rows of a band.
+struct ClsWgradParams {
+  const float* g;    // [n][D][D][D]      dL/dlogit
+  const float* a;    // [n][C][D][D][D]   head input
+  float* partial;    // [gridDim.x][C*27 + 1]
+  int32_t n;
+};
+
+template <int C, int D, int TYB>
+struct ClsWgradCfg {
+  static constexpr int SETT = C * 9;
+  static constexpr int NSET = 256 / SETT;
+  static constexpr int PI = D + 4;                 // tile col c <-> ix = c - 1
+  static constexpr int RA = TYB + 2;
+  static constexpr int A_FLOATS = C * 3 * RA * PI;
+  static constexpr int G_FLOATS = TYB * D;
+  static constexpr int NW = C * 27;
+  static constexpr int OUT_FLOATS = NW + 1;
+  static constexpr int RED_FLOATS = NSET * NW + 256;
+  static constexpr int SMEM_FLOATS = (A_FLOATS + G_FLOATS) > RED_FLOATS ? (A_FLOATS + G_FLOATS) : RED_FLOATS;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+  static constexpr int BANDS = D / TYB;
+  static_assert(SETT <= 256 && D % 8 == 0 && D % TYB == 0, "cls wgrad tiling");
+};
+
+template <int C, int D, int TYB>
+__global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
+  using G = ClsWgradCfg<C, D, TYB>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_a = smem;
+  float* s_g = smem + G::A_FLOATS;
+  const int tid = threadIdx.x;
+  const bool active = tid < G::NSET * G::SETT;
+  const int set = active ? tid / G::SETT : 0;
+  int r = active ? tid % G::SETT : 0;
+  const int ky = r % 3; r /= 3;
+  const int kz = r % 3; r /= 3;
+  const int ci = r;
+  float acc[3] = {0.f, 0.f, 0.f};
+  float dbacc = 0.f;
+
+  const int items = p.n * D * G::BANDS;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    int q = item;
+    const int band = q % G::BANDS; q /= G::BANDS;
+    const int z = q % D; q /= D;
+    const int b = q;
+    const int y0 = band * TYB;
+    __syncthreads();
+    {
+      const float* gb = p.g + (((size_t)b * D + z) * D + y0) * D;
+      for (int i = tid; i < G::G_FLOATS / 4; i += 256)
+        reinterpret_cast<float4*>(s_g)[i] = __ldg(reinterpret_cast<const float4*>(gb) + i);
+      const float* ab = p.a + (size_t)b * C * D * D * D;
+      for (int i = tid; i < C * 3 * G::RA * G::PI; i += 256) {
+        int t = i;
+        const int c = t % G::PI; t /= G::PI;
+        const int rr = t % G::RA; t /= G::RA;
+        const int s = t % 3; t /= 3;
+        const int ch = t;
+        const int ix = c - 1, iy = y0 + rr - 1, iz = z + s - 1;
+        float v = 0.f;
+        if (ix >= 0 && ix < D && iy >= 0 && iy < D && iz >= 0 && iz < D)
+          v = __ldg(ab + (((size_t)ch * D + iz) * D + iy) * D + ix);
+        s_a[i] = v;
+      }
+    }
+    __syncthreads();
+    {
+      float s = 0.f;
+      for (int i = tid; i < G::G_FLOATS; i += 256) s += s_g[i];
+      dbacc += s;
+    }
+    if (active) {
+      const float* ab = s_a + ((ci * 3 + kz) * G::RA + ky) * G::PI;
+      for (int rr = set; rr < TYB; rr += G::NSET) {
+#pragma unroll
+        for (int xo = 0; xo < D / 8; ++xo) {
+          const float* ar = ab + rr * G::PI + 8 * xo;
+          const float4 a0 = *reinterpret_cast<const float4*>(ar);
+          const float4 a1 = *reinterpret_cast<const float4*>(ar + 4);
+          const float2 a2 = *reinterpret_cast<const float2*>(ar + 8);
+          const float av[10] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+          const float4 g0 = *reinterpret_cast<const float4*>(s_g + rr * D + 8 * xo);
+          const float4 g1 = *reinterpret_cast<const float4*>(s_g + rr * D + 8 * xo + 4);
+          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc[kx] = fmaf(gv[j], av[j + kx], acc[kx]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* red = smem;
+  if (active) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) red[set * G::NW + ci * 27 + kz * 9 + ky * 3 + kx] = acc[kx];
+  }
+  red[G::NSET * G::NW + tid] = dbacc;
+  __syncthreads();
+  float* out = p.partial + (size_t)blockIdx.x * G::OUT_FLOATS;
+  for (int i = tid; i < G::NW; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < G::NSET; ++t) s += red[t * G::NW + i];
+    out[i] = s;
+  }
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 256; ++i) s += red[G::NSET * G::NW + i];
+    out[G::NW] = s;
+  }
+}
+
+// IGDN parameter gradients, one CTA per block:
+//   n_i = sqrt(beta_i + sum_j gamma_ij x_j^2),  t_i = g_i x_i / (2 n_i)
+//   dbeta_i = sum_pos t_i,  dgamma_ij = sum_pos t_i x_j^2
+// partial[b][C*C + C] = (dgamma, dbeta) of block b.
+struct IgdnParamParams {
+  const float* x;      // [n][C][64]
+  const float* g;      // [n][C][64]  dL/dy
+  const float* beta;   // [C]
+  const float* gamma;  // [C][C]
+  float* partial;      // [n][C*C + C]
+  int32_t n, C;
+};
+__global__ void __launch_bounds__(256) k_igdn_param(IgdnParamParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = p.C;
+  float* sx2 = smem;             // [C][64]  x^2
+  float* st = smem + C * 64;     // [C][64]  t
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xb = p.x + (size_t)b * C * 64;
+  const float* gb = p.g + (size_t)b * C * 64;
+  for (int i = tid; i < C * 64; i += 256) {
+    const float v = xb[i];
+    sx2[i] = v * v;
+  }
+  __syncthreads();
+  for (int i = tid; i < C * 64; i += 256) {
+    const int c = i >> 6, pos = i & 63;
+    float nn = p.beta[c];
+    for (int j = 0; j < C; ++j) nn = fmaf(p.gamma[c * C + j], sx2[j * 64 + pos], nn);
+    st[i] = gb[i] * xb[i] / (2.f * sqrtf(nn));
+  }
+  __syncthreads();
+  float* out = p.partial + (size_t)b * (C * C + C);
+  for (int e = tid; e < C * C + C; e += 256) {
+    float s = 0.f;
+    if (e < C * C) {
+      const int i = e / C, j = e % C;
+      for (int pos = 0; pos < 64; ++pos) s = fmaf(st[i * 64 + pos], sx2[j * 64 + pos], s);
+    } else {
+      const int i = e - C * C;
+      for (int pos = 0; pos < 64; ++pos) s += st[i * 64 + pos];
+    }
+    out[e] = s;
+  }
+}
+
+}  // namespace fast
+}  // namespace nvf

@@ -22,6 +22,7 @@ struct LayerParams {
   const float* add;   // same layout as out, added before act/mask, or null
   const float* mask;  // same layout as out: out = mask > 0 ? out : 0, or null
   int32_t n, CI, CO, Din, inPitch, Dout, outPitch, P, act, op;
+  float* out2;        // optional second copy of the output (same layout) or null
 };
 
 template <int COT>
@@ -62,6 +63,7 @@ struct LayerKernel {
           else if (p.act == ACT_SIGMOID) v = sigmoidf(v);
           if (p.mask) v = p.mask[o + j] > 0.f ? v : 0.f;
           p.out[o + j] = v;
+          if (p.out2) p.out2[o + j] = v;
         }
       }
     }
@@ -330,7 +332,7 @@ struct LossParams {
   float* g_out;       // or null
   float* g_cls1;
   float* g_cls0;
-  double* partial;    // [n][NVF_LOSS_SUMS]
+  double* partial;    // [n * kLossChunks][NVF_LOSS_SUMS]
   float alpha_main, alpha_aux, thh_metric;
   int32_t n;
 };
@@ -347,10 +349,12 @@ NVF_HD void focal_term(float p, bool occ, float a_occ, float a_emp, float w, flo
   dldp = clamped ? 0.f : (occ ? dF : -dF);
 }
 
+constexpr int kLossChunks = 8;  // CTAs per block: chunk c covers main-head slices 4c..4c+3 and the aux voxels below them
 struct LossBlock {
   // smem: kThreads * NVF_LOSS_SUMS doubles
   template <class Env>
-  static NVF_HD void run(Env& env, const LossParams& p, double* sm, int b) {
+  static NVF_HD void run(Env& env, const LossParams& p, double* sm, int bc) {
+    const int b = bc / kLossChunks, chunk = bc % kLossChunks;
     env.phase([&](int tid, int&) {
       double s[NVF_LOSS_SUMS];
       for (int i = 0; i < NVF_LOSS_SUMS; ++i) s[i] = 0.0;
@@ -359,7 +363,7 @@ struct LossBlock {
       const float* gt = p.gt + (int64_t)b * kVox;
       const float* dist = p.dist + (int64_t)b * kVox;
       const float* out = p.out + (int64_t)b * kVox;
-      for (int v = tid; v < kVox; v += kThreads) {
+      for (int v = chunk * (kVox / kLossChunks) + tid; v < (chunk + 1) * (kVox / kLossChunks); v += kThreads) {
         const bool occ = gt[v] != 0.f;
         const float pr = out[v], d = dist[v];
         float l, g;
@@ -371,7 +375,7 @@ struct LossBlock {
         else { s[8] += 1.0; if (!(pr > 0.5f)) s[7] += 1.0; }
       }
       // 16^3 head (cls1): GT = max over 2x2x2
-      for (int v = tid; v < 4096; v += kThreads) {
+      for (int v = chunk * (4096 / kLossChunks) + tid; v < (chunk + 1) * (4096 / kLossChunks); v += kThreads) {
         const int z = v >> 8, y = (v >> 4) & 15, x = v & 15;
         bool occ = false;
         for (int dz = 0; dz < 2; ++dz)
@@ -387,7 +391,7 @@ struct LossBlock {
         else { s[16] += 1.0; if (!(pr > 0.5f)) s[15] += 1.0; }
       }
       // 8^3 head (cls0): GT = max over 4x4x4
-      for (int v = tid; v < 512; v += kThreads) {
+      for (int v = chunk * (512 / kLossChunks) + tid; v < (chunk + 1) * (512 / kLossChunks); v += kThreads) {
         const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
         bool occ = false;
         for (int dz = 0; dz < 4; ++dz)
@@ -411,7 +415,7 @@ struct LossBlock {
       });
     }
     env.phase([&](int tid, int&) {
-      if (tid < NVF_LOSS_SUMS) p.partial[(int64_t)b * NVF_LOSS_SUMS + tid] = sm[tid * kThreads];
+      if (tid < NVF_LOSS_SUMS) p.partial[(int64_t)bc * NVF_LOSS_SUMS + tid] = sm[tid * kThreads];
     });
   }
 };

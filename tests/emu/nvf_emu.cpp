@@ -55,6 +55,16 @@ struct EmuLauncher {
       EmitBlock<EmuEnv<int>>::run(env, p, sm.data(), b);
     }
   }
+  // the shared-memory tiled CUDA kernels have no emulated counterpart: the generic kernels run instead
+  bool fast_layer(const LayerParams&) { return false; }
+  bool fast_wgrad(const WgradParams&, const ChanSumParams&) { return false; }
+  bool fast_igdn_param(const IgdnParams&) { return false; }
+  bool fast_stem_fwd(const NvfDesc&, const NvfWeights&, const float*, const float*, const float*, const float*, int,
+                     float*, float*, float*, float*, float*) { return false; }
+  bool fast_stem_bwd(const NvfDesc&, const NvfWeights&, const float*, int, const float*, const float*, const float*,
+                     const NvfWeightGrads*, float*) { return false; }
+  void set_partial(float*, size_t) {}
+  void flush_reduce() {}
   template <int COT>
   void layer(const LayerParams& p) {
     const int grid = 7;
