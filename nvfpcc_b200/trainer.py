@@ -1,0 +1,158 @@
+"""Host-sync-free training steps for the NVF path.
+
+`WeightStep` is the body of the reference's weight loop (train(), NVFPCC.py:149-223)
+and `EmbeddingStep` the once-per-epoch embedding update (NVFPCC.py:225-251), with
+
+* every scalar the reference reads back with `.item()` (NVFPCC.py:190-221) kept on the
+  device in one small `stats` tensor that the caller may read whenever it wants,
+* the whole step - fused decoder forward, fused rate-distortion loss, fused backward,
+  the tiny parameter-side torch ops, the NCCL all-reduce of the shared-weight gradient
+  and Adam - captured once in a CUDA graph and replayed (launch-bound otherwise: a
+  16-block step is ~0.3 ms of FP32 work but ~800 kernel launches),
+* results-neutral skipping of gradients the reference computes and then discards
+  (d/d-emb in the weight loop, all weight gradients in the embedding loop).
+
+The optimisation trajectory is the reference's: same loss, same Adam, same RNG
+distributions (the RNG *stream* differs, as it does between any two runs of the reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import dist as D
+from . import ops
+
+STAT_NAMES = ("loss", "bce", "ms0", "ms1", "b_latent", "b_net", "n_pts")
+
+
+def _loss_terms(net, emb, gt, dst, q, n_total, lmbda, w1, w2, focal_alpha, n_pts=None):
+    """NVFPCC.py:154-196 on the fused ops.  Returns (loss, stats[7], sums[20])."""
+    if n_pts is None:
+        n_pts = D.allreduce_sum_(gt.sum())                       # batch-global (NVFPCC.py:154,161)
+    out, cls_list, net_bits, latent_bits = net(emb, "train", q)
+    bce, ms0, ms1, sums = ops.rd_distortion(out, cls_list[1], cls_list[0], gt, dst, focal_alpha, 0.85, 0.6)
+    b_latent = latent_bits.sum() / n_pts
+    b_net = net_bits.sum() / n_total
+    loss = bce + ms0 + ms1 + lmbda * (b_latent * w1 + b_net * w2)
+    stats = torch.stack([loss.detach(), bce.detach(), ms0.detach(), ms1.detach(), b_latent.detach(),
+                         b_net.detach(), n_pts.detach().float()])
+    return loss, stats, sums
+
+
+class WeightStep:
+    """One minibatch update of the shared decoder weights (NVFPCC.py:149-223).
+
+    step(emb_batch, gt, dist) copies the batch into static device buffers (host tensors are
+    fine - pinned memory makes the copies asynchronous), replays the captured graph and returns
+    the device-resident stats tensor (see STAT_NAMES) - no host synchronisation."""
+
+    def __init__(self, net, opt: torch.optim.Optimizer, batch: int, n_total: float, lmbda: float, w1: float,
+                 w2: float, focal_alpha: float = 0.9, use_graph: bool = True, device=None):
+        self.net, self.opt = net, opt
+        self.hp = dict(n_total=float(n_total), lmbda=float(lmbda), w1=float(w1), w2=float(w2),
+                       focal_alpha=float(focal_alpha))
+        dev = device if device is not None else next(net.parameters()).device
+        ch = net.reconstructor.in_channels
+        self.emb = torch.zeros(batch, ch, 2, 2, 2, device=dev)
+        self.gt = torch.zeros(batch, 1, 32, 32, 32, device=dev)
+        self.dist = torch.zeros(batch, 1, 32, 32, 32, device=dev)
+        self.stats = torch.zeros(len(STAT_NAMES), device=dev)
+        self.sums = torch.zeros(ops._lib.NVF_LOSS_SUMS, dtype=torch.float64, device=dev)
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        if use_graph:
+            for g in opt.param_groups:
+                if not g.get("capturable", False):
+                    raise ValueError("WeightStep(use_graph=True) needs an optimizer built with capturable=True")
+
+    def _body(self, q: int):
+        self.opt.zero_grad(set_to_none=True)
+        loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q, **self.hp)
+        loss.backward()
+        D.allreduce_grads_(self.net.parameters())                # ONE all-reduce of the shared weights
+        self.opt.step()
+        self.stats.copy_(stats)
+        self.sums.copy_(sums)
+
+    def _capture(self, q: int):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            state = self._snapshot()
+            for _ in range(3):                                   # warm-up: allocator, lazy init, kernel attributes
+                self._body(q)
+            self._restore(state)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        b = ops._lib.cuda_binding()
+        n0 = b.launch_count()
+        with torch.cuda.graph(g):
+            self._body(q)
+        self.launches_per_step = b.launch_count() - n0           # hand-written kernels inside one replay
+        self._restore(state)                                     # capture does not run, but keep state exact
+        self._graphs[q] = g
+
+    def _snapshot(self):
+        import copy
+        return [p.detach().clone() for p in self.net.parameters()], copy.deepcopy(self.opt.state_dict())
+
+    def _restore(self, state):
+        params, opt_sd = state
+        with torch.no_grad():
+            for p, s in zip(self.net.parameters(), params):
+                p.copy_(s)
+        # restore optimizer tensors IN PLACE (the captured graph holds their addresses)
+        cur = self.opt.state_dict()
+        for k, st in opt_sd["state"].items():
+            for name, v in st.items():
+                if torch.is_tensor(v) and k in cur["state"]:
+                    cur["state"][k][name].copy_(v)
+        if not opt_sd["state"]:
+            for st in self.opt.state.values():
+                for name, v in st.items():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def step(self, emb_batch: torch.Tensor, gt: torch.Tensor, dist_: torch.Tensor, q: int = 1) -> torch.Tensor:
+        self.emb.copy_(emb_batch.detach(), non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        self.dist.copy_(dist_, non_blocking=True)
+        if not self.use_graph:
+            self._body(q)
+            return self.stats
+        if q not in self._graphs:
+            self._capture(q)
+        self._graphs[q].replay()
+        return self.stats
+
+
+class EmbeddingStep:
+    """The once-per-epoch update of all embeddings (NVFPCC.py:225-251): one full-batch forward +
+    backward w.r.t. the embeddings only (the weight gradients of this pass are discarded by the
+    reference, so they are not computed), rank-local: no collective."""
+
+    def __init__(self, net, emb: torch.Tensor, opt_emb: torch.optim.Optimizer, n_total: float, lmbda: float,
+                 w1: float, w2: float, focal_alpha: float = 0.9):
+        self.net, self.emb, self.opt = net, emb, opt_emb
+        self.hp = dict(n_total=float(n_total), lmbda=float(lmbda), w1=float(w1), w2=float(w2),
+                       focal_alpha=float(focal_alpha))
+
+    def step(self, gt: torch.Tensor, dist_: torch.Tensor, q: int, n_pts: Optional[torch.Tensor] = None):
+        self.opt.zero_grad(set_to_none=True)
+        req = [p.requires_grad for p in self.net.parameters()]
+        for p in self.net.parameters():
+            p.requires_grad_(False)
+        try:
+            if n_pts is None:
+                n_pts = torch.as_tensor(self.hp["n_total"], device=gt.device)   # NVFPCC.py:230,319
+            loss, stats, _ = _loss_terms(self.net, self.emb, gt, dist_, q, n_pts=n_pts, **self.hp)
+            loss.backward()
+        finally:
+            for p, r in zip(self.net.parameters(), req):
+                p.requires_grad_(r)
+        self.opt.step()
+        return stats

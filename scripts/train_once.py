@@ -10,6 +10,7 @@ ap.add_argument("--chanstr", default="8,16,8,8")
 ap.add_argument("--resolution", type=int, default=1024)
 ap.add_argument("--train-blocks", type=int, default=32)
 ap.add_argument("--warm", type=int, default=2)
+ap.add_argument("--no-graph", action="store_true")
 a = ap.parse_args()
 torch.cuda.set_device(0)
 pts, origins = bench.make_cloud(a.resolution)

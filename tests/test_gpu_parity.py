@@ -99,3 +99,66 @@ def test_backward_flags_skip_work(gpu, golden_A):
     assert nol is None
     for k in gw_full:
         assert torch.equal(gw_full[k], gw_only[k]), k
+
+
+def _make_step(graph):
+    from nvfpcc_b200 import network, synth, trainer
+    network.set_seed(synth.synthetic_seed())
+    net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8").cuda()
+    net.entropy_coder.noise_scale = 0.0
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+    return net, trainer.WeightStep(net, opt, batch=2, n_total=849338.0, lmbda=200.0, w1=10.0, w2=57.0, use_graph=graph)
+
+
+def test_graphed_weight_step_equals_eager(gpu, golden_A):
+    """The CUDA-graph replay of the weight-loop step (NVFPCC.py:149-223) must walk the same
+    trajectory as the eager step: q=2 and zero latent noise make both deterministic."""
+    gt = torch.from_numpy(golden_A["tr_gt"]).float().cuda()
+    dist = torch.from_numpy(golden_A["tr_dist"]).float().cuda()
+    emb = torch.ones(2, 3, 2, 2, 2).cuda()
+    stats = {}
+    params = {}
+    for graph in (False, True):
+        net, ws = _make_step(graph)
+        hist = []
+        for i in range(4):
+            hist.append(ws.step(emb, gt if i % 2 == 0 else gt.flip(0), dist if i % 2 == 0 else dist.flip(0), q=2).clone())
+        stats[graph] = torch.stack(hist).cpu()
+        params[graph] = [p.detach().cpu().clone() for p in net.parameters()]
+        if graph:
+            assert ws.launches_per_step > 20
+    assert torch.isfinite(stats[True]).all()
+    np.testing.assert_allclose(stats[True].numpy(), stats[False].numpy(), rtol=1e-5, atol=1e-6)
+    for a, b in zip(params[True], params[False]):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-6)
+    # the loss of the 3rd visit of a batch is below its 1st visit (Adam is actually stepping)
+    assert stats[True][2, 0] < stats[True][0, 0]
+
+
+def test_weight_step_matches_oracle_step(gpu, golden_A):
+    """One eager WeightStep == one oracle step (loss terms and post-Adam weights)."""
+    from nvfpcc_b200 import network, synth
+    gt = torch.from_numpy(golden_A["tr_gt"]).float()
+    dist = torch.from_numpy(golden_A["tr_dist"]).float()
+    net, ws = _make_step(False)
+    sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    emb = torch.ones(2, 3, 2, 2, 2)
+    st = ws.step(emb.cuda(), gt.cuda(), dist.cuda(), q=2).cpu()
+    # oracle: same state, zero latent noise (x + (0.5 - 0.5)), autograd + Adam
+    sd = {k: v.clone() for k, v in sd0.items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if not k.endswith(("_init", "pedestal"))}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    res = O.net_forward(emb, sd, "train", 2, latent_noise=torch.full((2, 3, 2, 2, 2), 0.5))
+    L = O.train_loss(res, gt, dist, gt.sum(), 849338.0, 200.0, 10.0, 57.0)
+    L["loss"].backward()
+    opt.step()
+    assert abs(st[0].item() - L["loss"].item()) <= 1e-4 * abs(L["loss"].item())
+    new = net.state_dict()
+    for k, v in params.items():
+        got = new[k].detach().cpu()
+        # Adam's first step moves every weight by ~lr * sign(grad): compare the update direction where it is defined
+        d_got, d_ref = got - sd0[k], v.detach() - sd0[k]
+        big = d_ref.abs() > 5e-4
+        flips = (torch.sign(d_got[big]) != torch.sign(d_ref[big])).float().mean().item() if big.any() else 0.0
+        assert flips <= 2e-3, (k, flips)
+        np.testing.assert_allclose(got.numpy(), v.detach().numpy(), rtol=0, atol=2.1e-3)
