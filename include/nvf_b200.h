@@ -169,6 +169,47 @@ int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* la
                        const NvfWeightGrads* gw, float* g_latent, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/*
+ * Parameter-side transforms of the training step, fused (forward + backward).
+ * Replaces, per call, the ~250 small framework launches behind
+ *   Q{ConvTranspose3d,Conv3d}.forward / IConv3d.forward weight preparation
+ *     (W_eff = Q_q(kernel) + kernel_init, b_eff = b + b_init; utils/network.py:606-620, 669-686, 735-740),
+ *   the IGDN reparametrisation (gdn_3d.py:143-150) and
+ *   net_bits = [likelihood_model(bypass_round16(p)) for p in get_q_params()] (utils/network.py:4777-4778, 287-305).
+ * Layer order of the arrays: up0 conv0 up1 conv1 up2 conv2 conv2_cls conv1_cls conv0_cls
+ * (the first NVF_NUM_QUANT are the quantised ones).
+ */
+#define NVF_NUM_CONV 9
+#define NVF_NUM_QUANT 7
+#define NVF_PARAM_WS_BYTES (64 * 1024)
+typedef struct NvfParamSet {
+  const float* kernel[NVF_NUM_CONV];       /* trainable deltas, native PyTorch layouts   */
+  const float* kernel_init[NVF_NUM_CONV];  /* seed-derived buffers                       */
+  const float* b[NVF_NUM_CONV];
+  const float* b_init[NVF_NUM_CONV];
+  const float* igdn_beta;                  /* raw (c0)                                   */
+  const float* igdn_gamma;                 /* raw (c0,c0)                                */
+  const float* lik_sigma;                  /* likelihood_model.sigma (1)                 */
+  const float* lik_mu;                     /* likelihood_model.mu (1)                    */
+} NvfParamSet;
+typedef struct NvfParamGrads {
+  float* kernel[NVF_NUM_CONV];
+  float* b[NVF_NUM_CONV];
+  float* igdn_beta; float* igdn_gamma; float* lik_sigma; float* lik_mu;
+} NvfParamGrads;
+/*   q      0 none, 1 additive U(-1/32,1/32) noise, 2 straight-through round16
+ *   noise  U(0,1) samples, one per element of the 7 quantised kernels in layer order (q == 1), else NULL
+ *   eff    OUT: the 20 effective tensors (same struct as the weight gradients: plain float*)
+ *   net_bits OUT [NVF_NUM_QUANT] */
+int nvf_param_prep(const NvfDesc* desc, const NvfParamSet* params, int q, const float* noise, float beta_bound,
+                   float gamma_bound, float pedestal, const NvfWeightGrads* eff, float* net_bits, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/*   g_eff      gradients w.r.t. the 20 effective tensors, g_net_bits [NVF_NUM_QUANT]
+ *   out        OUT: gradients w.r.t. kernel / b / raw IGDN beta,gamma / likelihood sigma,mu */
+int nvf_param_prep_backward(const NvfDesc* desc, const NvfParamSet* params, float beta_bound, float gamma_bound,
+                            const NvfWeights* g_eff, const float* g_net_bits, const NvfParamGrads* out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* FP32 FFMA throughput micro-benchmark (roofline denominator):
  * runs `iters` dependent-chain FFMA batches on every SM; returns the number of
  * FLOPs executed in flops_out.  The caller times it with CUDA events. */

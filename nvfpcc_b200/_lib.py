@@ -31,8 +31,10 @@ NVF_LOSS_CHUNKS = 8   # CTAs per block of nvf_loss_seeds (workspace: 8 * NVF_LOS
 EXPORTS = (
     "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_launch_count", "nvf_has_fused_decode", "nvf_workspace_bytes",
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
-    "nvf_ffma_microbench",
+    "nvf_ffma_microbench", "nvf_param_prep", "nvf_param_prep_backward",
 )
+CONV_LAYERS = ("up0", "conv0", "up1", "conv1", "up2", "conv2", "cls2", "cls1", "cls0")   # NvfParamSet order
+NVF_NUM_CONV, NVF_NUM_QUANT, NVF_PARAM_WS_BYTES = 9, 7, 64 * 1024
 
 
 class NvfDesc(C.Structure):
@@ -56,6 +58,17 @@ def weight_shapes(ch: int, channels: Sequence[int]) -> Dict[str, tuple]:
         "conv2_w": (c3, c3, 4, 4, 4), "conv2_b": (c3,), "cls2_w": (1, c3, 3, 3, 3), "cls2_b": (1,),
         "cls1_w": (1, c2, 3, 3, 3), "cls1_b": (1,), "cls0_w": (1, c1, 3, 3, 3), "cls0_b": (1,),
     }
+
+
+class NvfParamSet(C.Structure):
+    _fields_ = [("kernel", C.c_void_p * 9), ("kernel_init", C.c_void_p * 9), ("b", C.c_void_p * 9),
+                ("b_init", C.c_void_p * 9), ("igdn_beta", C.c_void_p), ("igdn_gamma", C.c_void_p),
+                ("lik_sigma", C.c_void_p), ("lik_mu", C.c_void_p)]
+
+
+class NvfParamGrads(C.Structure):
+    _fields_ = [("kernel", C.c_void_p * 9), ("b", C.c_void_p * 9), ("igdn_beta", C.c_void_p),
+                ("igdn_gamma", C.c_void_p), ("lik_sigma", C.c_void_p), ("lik_mu", C.c_void_p)]
 
 
 class NvfError(RuntimeError):
@@ -94,6 +107,10 @@ class Binding:
         L.nvf_train_backward.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfWeights), vp, C.c_int64, vp, vp, vp, C.c_int,
                                          C.POINTER(NvfWeightGrads), vp, vp, C.c_size_t, vp]
         L.nvf_ffma_microbench.argtypes = [C.c_int, C.c_int64, vp, C.POINTER(C.c_double), vp]
+        L.nvf_param_prep.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfParamSet), C.c_int, vp, C.c_float, C.c_float,
+                                     C.c_float, C.POINTER(NvfWeightGrads), vp, vp, C.c_size_t, vp]
+        L.nvf_param_prep_backward.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfParamSet), C.c_float, C.c_float,
+                                              C.POINTER(NvfWeights), vp, C.POINTER(NvfParamGrads), vp, C.c_size_t, vp]
         if L.nvf_abi_version() != 1:
             raise NvfError("ABI version mismatch in %s" % path)
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -233,6 +250,69 @@ class Binding:
                                      _ptr(g[1]), _ptr(g[2]), _ptr(ws), ws.numel(), self._stream(dev))
         self.check(rc, "nvf_loss_seeds")
         return sums, g
+
+    # ---- fused parameter-side transforms --------------------------------------------------------
+    @staticmethod
+    def _param_set(raw: Dict[str, torch.Tensor]):
+        """raw: {layer}_{kernel,kernel_init,b,b_init} for layer in CONV_LAYERS + igdn_beta/igdn_gamma/lik_sigma/lik_mu."""
+        ps = NvfParamSet()
+        keep = []
+        for i, name in enumerate(CONV_LAYERS):
+            for field in ("kernel", "kernel_init", "b", "b_init"):
+                t = raw["%s_%s" % (name, field)].detach().contiguous()
+                keep.append(t)
+                getattr(ps, field)[i] = t.data_ptr()
+        for field in ("igdn_beta", "igdn_gamma", "lik_sigma", "lik_mu"):
+            t = raw[field].detach().contiguous()
+            keep.append(t)
+            setattr(ps, field, t.data_ptr())
+        return ps, keep
+
+    def param_prep(self, desc: NvfDesc, raw: Dict[str, torch.Tensor], q: int, noise: Optional[torch.Tensor],
+                   beta_bound: float, gamma_bound: float, pedestal: float):
+        dev = raw["lik_sigma"].device
+        ps, keep = self._param_set(raw)
+        eff: Dict[str, torch.Tensor] = {}
+        est = NvfWeightGrads()
+        for name in CONV_LAYERS:
+            eff[name + "_w"] = torch.empty_like(raw[name + "_kernel"], memory_format=torch.contiguous_format)
+            eff[name + "_b"] = torch.empty_like(raw[name + "_b"])
+        eff["igdn_beta"] = torch.empty_like(raw["igdn_beta"])
+        eff["igdn_gamma"] = torch.empty_like(raw["igdn_gamma"], memory_format=torch.contiguous_format)
+        for name in WEIGHT_FIELDS:
+            setattr(est, name, eff[name].data_ptr())
+        bits = torch.empty(NVF_NUM_QUANT, dtype=torch.float32, device=dev)
+        ws = self.cached_workspace(NVF_PARAM_WS_BYTES, dev, "param")
+        rc = self.lib.nvf_param_prep(C.byref(desc), C.byref(ps), int(q), _ptr(noise), float(beta_bound),
+                                     float(gamma_bound), float(pedestal), C.byref(est), _ptr(bits), _ptr(ws),
+                                     ws.numel(), self._stream(dev))
+        self.check(rc, "nvf_param_prep")
+        del keep
+        return eff, bits
+
+    def param_prep_backward(self, desc: NvfDesc, raw: Dict[str, torch.Tensor], beta_bound: float, gamma_bound: float,
+                            g_eff: Dict[str, torch.Tensor], g_bits: torch.Tensor):
+        dev = raw["lik_sigma"].device
+        ps, keep = self._param_set(raw)
+        gst, keep2 = self.pack_weights(g_eff, dev, need_aux=True)
+        out: Dict[str, torch.Tensor] = {}
+        pg = NvfParamGrads()
+        for i, name in enumerate(CONV_LAYERS):
+            out[name + "_kernel"] = torch.empty_like(raw[name + "_kernel"], memory_format=torch.contiguous_format)
+            out[name + "_b"] = torch.empty_like(raw[name + "_b"])
+            pg.kernel[i] = out[name + "_kernel"].data_ptr()
+            pg.b[i] = out[name + "_b"].data_ptr()
+        for field in ("igdn_beta", "igdn_gamma", "lik_sigma", "lik_mu"):
+            out[field] = torch.empty_like(raw[field], memory_format=torch.contiguous_format)
+            setattr(pg, field, out[field].data_ptr())
+        g_bits = g_bits.detach().contiguous().float()
+        ws = self.cached_workspace(NVF_PARAM_WS_BYTES, dev, "param_bwd")
+        rc = self.lib.nvf_param_prep_backward(C.byref(desc), C.byref(ps), float(beta_bound), float(gamma_bound),
+                                              C.byref(gst), _ptr(g_bits), C.byref(pg), _ptr(ws), ws.numel(),
+                                              self._stream(dev))
+        self.check(rc, "nvf_param_prep_backward")
+        del keep, keep2
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.nvf_launch_count())

@@ -10,6 +10,7 @@
 #include "nvf_fast_convt.cuh"
 #include "nvf_fast_misc.cuh"
 #include "nvf_fast_stem.cuh"
+#include "nvf_fast_params.cuh"
 
 using namespace nvf;
 
@@ -550,6 +551,110 @@ int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* la
   if (l.init() != NVF_OK) return l.rc;
   return Api<DevLauncher>::train_backward(l, desc, w, latent, n_blocks, g_out, g_cls1, g_cls0, flags, gw, g_latent,
                                           workspace, workspace_bytes);
+}
+
+namespace {
+// element counts of the 9 conv kernels / biases in NvfParamSet order
+void conv_sizes(const NvfDesc& d, int (&nw)[NVF_NUM_CONV], int (&nb)[NVF_NUM_CONV]) {
+  const int w[NVF_NUM_CONV] = {d.ch * d.c0 * 125, d.c0 * d.c1 * 125, d.c1 * d.c2 * 125, d.c2 * d.c2 * 64, d.c2 * d.c3 * 125,
+                               d.c3 * d.c3 * 64,  d.c3 * 27,         d.c2 * 27,         d.c1 * 27};
+  const int b[NVF_NUM_CONV] = {d.c0, d.c1, d.c2, d.c2, d.c3, d.c3, 1, 1, 1};
+  for (int i = 0; i < NVF_NUM_CONV; ++i) { nw[i] = w[i]; nb[i] = b[i]; }
+}
+int fill_param_jobs(const NvfDesc& d, const NvfParamSet& ps, fast::ParamPrepParams& pp) {
+  int nw[NVF_NUM_CONV], nb[NVF_NUM_CONV];
+  conv_sizes(d, nw, nb);
+  int chunk = 0, noise0 = 0;
+  for (int l = 0; l < NVF_NUM_CONV; ++l) {
+    fast::ParamJob& J = pp.job[l];
+    if (!ps.kernel[l] || !ps.kernel_init[l] || !ps.b[l] || !ps.b_init[l]) return NVF_ERR_INVALID_ARG;
+    J.kernel = ps.kernel[l]; J.init = ps.kernel_init[l]; J.b = ps.b[l]; J.b_init = ps.b_init[l];
+    J.n = nw[l]; J.nb = nb[l];
+    J.chunk0 = chunk;
+    J.nchunks = (nw[l] + fast::kParamChunk - 1) / fast::kParamChunk;
+    chunk += J.nchunks;
+    J.noise0 = noise0;
+    if (l < NVF_NUM_QUANT) noise0 += nw[l];
+  }
+  pp.total_chunks = chunk;
+  pp.igdn_beta = ps.igdn_beta; pp.igdn_gamma = ps.igdn_gamma;
+  pp.lik_sigma = ps.lik_sigma; pp.lik_mu = ps.lik_mu;
+  pp.c0 = d.c0;
+  if (!ps.igdn_beta || !ps.igdn_gamma || !ps.lik_sigma || !ps.lik_mu) return NVF_ERR_INVALID_ARG;
+  if ((size_t)chunk * 3 * sizeof(float) > NVF_PARAM_WS_BYTES) return NVF_ERR_UNSUPPORTED;
+  return NVF_OK;
+}
+float* const* eff_slots_w(const NvfWeightGrads& e, float* (&w)[NVF_NUM_CONV], float* (&b)[NVF_NUM_CONV]) {
+  float* ws[NVF_NUM_CONV] = {e.up0_w, e.conv0_w, e.up1_w, e.conv1_w, e.up2_w, e.conv2_w, e.cls2_w, e.cls1_w, e.cls0_w};
+  float* bs[NVF_NUM_CONV] = {e.up0_b, e.conv0_b, e.up1_b, e.conv1_b, e.up2_b, e.conv2_b, e.cls2_b, e.cls1_b, e.cls0_b};
+  for (int i = 0; i < NVF_NUM_CONV; ++i) { w[i] = ws[i]; b[i] = bs[i]; }
+  return nullptr;
+}
+}  // namespace
+
+int nvf_param_prep(const NvfDesc* desc, const NvfParamSet* params, int q, const float* noise, float beta_bound,
+                   float gamma_bound, float pedestal, const NvfWeightGrads* eff, float* net_bits, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (!desc || !params || !eff || !net_bits || !workspace || q < 0 || q > 2) return NVF_ERR_INVALID_ARG;
+  if (q == 1 && !noise) return NVF_ERR_INVALID_ARG;
+  if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
+  if (workspace_bytes < NVF_PARAM_WS_BYTES) return NVF_ERR_WORKSPACE;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::ParamPrepParams pp{};
+  int rc = fill_param_jobs(*desc, *params, pp);
+  if (rc != NVF_OK) return rc;
+  float *w[NVF_NUM_CONV], *b[NVF_NUM_CONV];
+  eff_slots_w(*eff, w, b);
+  for (int i = 0; i < NVF_NUM_CONV; ++i) {
+    if (!w[i] || !b[i]) return NVF_ERR_INVALID_ARG;
+    pp.job[i].w_out = w[i]; pp.job[i].b_out = b[i];
+  }
+  if (!eff->igdn_beta || !eff->igdn_gamma) return NVF_ERR_INVALID_ARG;
+  pp.beta_out = eff->igdn_beta; pp.gamma_out = eff->igdn_gamma;
+  pp.noise = noise; pp.q = q;
+  pp.partial = (float*)workspace; pp.net_bits = net_bits;
+  pp.beta_bound = beta_bound; pp.gamma_bound = gamma_bound; pp.pedestal = pedestal;
+  fast::k_param_prep<false><<<pp.total_chunks + 1, 256, 0, l.st>>>(pp);
+  l.post();
+  fast::k_param_final<false><<<1, 32, 0, l.st>>>(pp);
+  l.post();
+  return l.rc;
+}
+
+int nvf_param_prep_backward(const NvfDesc* desc, const NvfParamSet* params, float beta_bound, float gamma_bound,
+                            const NvfWeights* g_eff, const float* g_net_bits, const NvfParamGrads* out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!desc || !params || !g_eff || !g_net_bits || !out || !workspace) return NVF_ERR_INVALID_ARG;
+  if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
+  if (workspace_bytes < NVF_PARAM_WS_BYTES) return NVF_ERR_WORKSPACE;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::ParamPrepParams pp{};
+  int rc = fill_param_jobs(*desc, *params, pp);
+  if (rc != NVF_OK) return rc;
+  const float* gw[NVF_NUM_CONV] = {g_eff->up0_w, g_eff->conv0_w, g_eff->up1_w, g_eff->conv1_w, g_eff->up2_w,
+                                   g_eff->conv2_w, g_eff->cls2_w, g_eff->cls1_w, g_eff->cls0_w};
+  const float* gb[NVF_NUM_CONV] = {g_eff->up0_b, g_eff->conv0_b, g_eff->up1_b, g_eff->conv1_b, g_eff->up2_b,
+                                   g_eff->conv2_b, g_eff->cls2_b, g_eff->cls1_b, g_eff->cls0_b};
+  for (int i = 0; i < NVF_NUM_CONV; ++i) {
+    if (!gw[i] || !gb[i] || !out->kernel[i] || !out->b[i]) return NVF_ERR_INVALID_ARG;
+    pp.job[i].g_w = gw[i]; pp.job[i].g_b = gb[i];
+    pp.job[i].w_out = out->kernel[i]; pp.job[i].b_out = out->b[i];
+  }
+  if (!g_eff->igdn_beta || !g_eff->igdn_gamma || !out->igdn_beta || !out->igdn_gamma || !out->lik_sigma || !out->lik_mu)
+    return NVF_ERR_INVALID_ARG;
+  pp.g_beta = g_eff->igdn_beta; pp.g_gamma = g_eff->igdn_gamma;
+  pp.beta_out = out->igdn_beta; pp.gamma_out = out->igdn_gamma;
+  pp.g_bits = g_net_bits;
+  pp.partial = (float*)workspace;
+  pp.g_sigma = out->lik_sigma; pp.g_mu = out->lik_mu;
+  pp.beta_bound = beta_bound; pp.gamma_bound = gamma_bound;
+  fast::k_param_prep<true><<<pp.total_chunks + 1, 256, 0, l.st>>>(pp);
+  l.post();
+  fast::k_param_final<true><<<1, 32, 0, l.st>>>(pp);
+  l.post();
+  return l.rc;
 }
 
 int nvf_ffma_microbench(int variant, int64_t iters, float* sink, double* flops_out, void* stream) {

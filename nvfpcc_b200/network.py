@@ -165,6 +165,7 @@ class _GDNBase(nn.Module):
     def __init__(self, ch, inverse=False, beta_min=1e-6, gamma_init=.1, reparam_offset=2 ** -18):
         super().__init__()
         ped = reparam_offset ** 2
+        self.reparam_pedestal = ped
         self.beta_bound = (beta_min + ped) ** .5
         self.gamma_bound = reparam_offset
         self.beta = nn.Parameter(torch.sqrt(torch.ones(ch) + ped))
@@ -313,9 +314,28 @@ class CompDecoder(nn.Module):
     def net_bits(self) -> torch.Tensor:
         return torch.stack([self.likelihood_model(bypass_round16(p)) for p in self.get_q_params()])
 
+    def raw_tensors(self) -> Dict[str, torch.Tensor]:
+        """The trainable tensors + seed buffers the fused parameter kernels read (ops.RAW_FIELDS)."""
+        raw: Dict[str, torch.Tensor] = {}
+        for name, key in (("up0", "up0"), ("conv0", "conv0"), ("up1", "up1"), ("conv1", "conv1"), ("up2", "up2"),
+                          ("conv2", "conv2"), ("conv2_cls", "cls2"), ("conv1_cls", "cls1"), ("conv0_cls", "cls0")):
+            m = getattr(self, name)
+            raw[key + "_kernel"], raw[key + "_kernel_init"], raw[key + "_b"], raw[key + "_b_init"] = (
+                m.kernel, m.kernel_init, m.b, m.b_init)
+        raw["igdn_beta"], raw["igdn_gamma"] = self.activation.beta, self.activation.gamma
+        raw["lik_sigma"], raw["lik_mu"] = self.likelihood_model.sigma, self.likelihood_model.mu
+        return raw
+
     def forward(self, x, q):
-        out, cls1, cls0 = ops.nvf_decoder(self.in_channels, self.channels, x, self.effective_weights(q))
-        return out, [cls0, cls1, out], self.net_bits()
+        if x.is_cuda:
+            # one fused kernel pair for every parameter-side transform + net_bits (nvf_param_prep)
+            w, net_bits = ops.decoder_params(self.in_channels, self.channels, q, self.raw_tensors(),
+                                             self.activation.beta_bound, self.activation.gamma_bound,
+                                             float(self.activation.reparam_pedestal))
+        else:
+            w, net_bits = self.effective_weights(q), self.net_bits()
+        out, cls1, cls0 = ops.nvf_decoder(self.in_channels, self.channels, x, w)
+        return out, [cls0, cls1, out], net_bits
 
     @torch.no_grad()
     def reconstruct(self, x, q=2):

@@ -119,3 +119,62 @@ def rd_distortion(out, cls1, cls0, gt, dist, alpha_main: float = 0.9, alpha_aux:
     ms0/ms1 = get_focal_dense on the 8^3 / 16^3 heads against max-pooled GT (NVFPCC.py:166-184);
     sums: see include/nvf_b200.h (sse/denom at thh_metric, tp/ap/tn/an of each head at 0.5)."""
     return _RdDistortionFn.apply(out, cls1, cls0, gt, dist, float(alpha_main), float(alpha_aux), float(thh_metric))
+
+
+RAW_FIELDS = tuple("%s_%s" % (l, f) for l in _lib.CONV_LAYERS for f in ("kernel", "kernel_init", "b", "b_init")) + (
+    "igdn_beta", "igdn_gamma", "lik_sigma", "lik_mu")
+
+
+class _ParamPrepFn(torch.autograd.Function):
+    """forward: nvf_param_prep; backward: nvf_param_prep_backward.  Inputs: the raw tensors in RAW_FIELDS
+    order; outputs: the 20 effective tensors in WEIGHT_FIELDS order + net_bits[7]."""
+
+    @staticmethod
+    def forward(ctx, ch, channels, q, noise, beta_bound, gamma_bound, pedestal, *raw):
+        b = _lib.cuda_binding()
+        rawd = dict(zip(RAW_FIELDS, raw))
+        if rawd["lik_sigma"].device.type != "cuda":
+            raise NvfError("decoder_params needs CUDA tensors; there is no CPU fallback")
+        eff, bits = b.param_prep(b.desc(ch, channels), rawd, q, noise, beta_bound, gamma_bound, pedestal)
+        ctx.args = (ch, tuple(channels), beta_bound, gamma_bound)
+        ctx.save_for_backward(*raw)
+        return tuple(eff[k] for k in WEIGHT_FIELDS) + (bits,)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        b = _lib.cuda_binding()
+        raw = ctx.saved_tensors
+        rawd = dict(zip(RAW_FIELDS, raw))
+        ch, channels, beta_bound, gamma_bound = ctx.args
+        g_eff = {}
+        for k, g, ref in zip(WEIGHT_FIELDS, grads[:-1], [None] * len(WEIGHT_FIELDS)):
+            g_eff[k] = g
+        shapes = _lib.weight_shapes(ch, channels)
+        dev = rawd["lik_sigma"].device
+        for k in WEIGHT_FIELDS:
+            if g_eff[k] is None:
+                g_eff[k] = torch.zeros(shapes[k], dtype=torch.float32, device=dev)
+            else:
+                g_eff[k] = g_eff[k].contiguous()
+        g_bits = grads[-1] if grads[-1] is not None else torch.zeros(_lib.NVF_NUM_QUANT, device=dev)
+        out = b.param_prep_backward(b.desc(ch, channels), rawd, beta_bound, gamma_bound, g_eff, g_bits)
+        res = []
+        for i, name in enumerate(RAW_FIELDS):
+            g = None
+            if ctx.needs_input_grad[7 + i]:
+                g = out.get(name)
+            res.append(g)
+        return (None,) * 7 + tuple(res)
+
+
+def decoder_params(ch: int, channels: Sequence[int], q: int, raw: Dict[str, torch.Tensor], beta_bound: float,
+                   gamma_bound: float, pedestal: float):
+    """Fused parameter-side transforms (see include/nvf_b200.h nvf_param_prep): raw tensors ->
+    (effective tensors dict, net_bits[7]); differentiable w.r.t. kernel / b / IGDN beta,gamma / likelihood sigma,mu."""
+    noise = None
+    if q == 1:
+        n = sum(raw[l + "_kernel"].numel() for l in _lib.CONV_LAYERS[:_lib.NVF_NUM_QUANT])
+        noise = torch.rand(n, device=raw["lik_sigma"].device, dtype=torch.float32)
+    outs = _ParamPrepFn.apply(int(ch), tuple(int(c) for c in channels), int(q), noise, float(beta_bound),
+                              float(gamma_bound), float(pedestal), *[raw[k] for k in RAW_FIELDS])
+    return dict(zip(WEIGHT_FIELDS, outs[:-1])), outs[-1]

@@ -164,4 +164,10 @@ int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* la
 }
 int nvf_ffma_microbench(int, int64_t, float*, double*, void*) { return NVF_ERR_NO_DEVICE; }
 
+
+// parameter-side fused kernels exist only in the CUDA library (the torch ops they replace are the CPU reference)
+int nvf_param_prep(const NvfDesc*, const NvfParamSet*, int, const float*, float, float, float, const NvfWeightGrads*,
+                   float*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_param_prep_backward(const NvfDesc*, const NvfParamSet*, float, float, const NvfWeights*, const float*,
+                            const NvfParamGrads*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
 }  // extern "C"

@@ -162,3 +162,61 @@ def test_weight_step_matches_oracle_step(gpu, golden_A):
         flips = (torch.sign(d_got[big]) != torch.sign(d_ref[big])).float().mean().item() if big.any() else 0.0
         assert flips <= 2e-3, (k, flips)
         np.testing.assert_allclose(got.numpy(), v.detach().numpy(), rtol=0, atol=2.1e-3)
+
+
+@pytest.mark.parametrize("q", [0, 1, 2])
+def test_fused_param_prep_matches_torch_path(gpu, q):
+    """nvf_param_prep (+ backward) against the torch ops it replaces (utils/network.py:606-620 weight
+    preparation, gdn_3d.py:143-150 reparametrisation, :4777-4778 net_bits) incl. autograd."""
+    from nvfpcc_b200 import network, ops, synth, _lib
+    fx = fixture_inputs("A")
+    network.set_seed(synth.synthetic_seed())
+    nets = []
+    for _ in range(2):
+        network.seed_ptr = 0
+        n = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8")
+        n.load_state_dict(fx["sd"])          # perturbed state: non-trivial kernels, sigma, mu, beta, gamma
+        nets.append(n.cuda().reconstructor)
+    ref, fus = nets
+    with torch.no_grad():                    # push some IGDN entries below their bounds (LowerBound branches)
+        for r in (ref, fus):
+            r.activation.gamma[0, 1] = 1e-7
+            r.activation.gamma[2, 3] = -0.5
+            r.activation.beta[1] = 1e-4
+    g = torch.Generator(device="cuda").manual_seed(5)
+    nq = sum(p.numel() for p in ref.get_q_params())
+    noise = torch.rand(nq, device="cuda", generator=g) if q == 1 else None
+    # torch path with the same noise
+    w_ref = {}
+    off = 0
+    for name, key in (("up0", "up0"), ("conv0", "conv0"), ("up1", "up1"), ("conv1", "conv1"), ("up2", "up2"),
+                      ("conv2", "conv2"), ("conv2_cls", "cls2")):
+        m = getattr(ref, name)
+        k = m.kernel
+        if q == 1:
+            k = k + (noise[off:off + k.numel()].view_as(k) - 0.5) * (1 / 16)
+        elif q == 2:
+            k = network.bypass_round16(k)
+        off += m.kernel.numel()
+        w_ref[key + "_w"], w_ref[key + "_b"] = k + m.kernel_init, m.b + m.b_init
+    w_ref["cls1_w"], w_ref["cls1_b"] = ref.conv1_cls.effective()
+    w_ref["cls0_w"], w_ref["cls0_b"] = ref.conv0_cls.effective()
+    w_ref["igdn_beta"], w_ref["igdn_gamma"] = ref.activation.effective()
+    bits_ref = ref.net_bits()
+    outs = ops._ParamPrepFn.apply(3, (8, 16, 8, 8), q, noise, float(fus.activation.beta_bound),
+                                  float(fus.activation.gamma_bound), float(fus.activation.reparam_pedestal),
+                                  *[fus.raw_tensors()[k] for k in ops.RAW_FIELDS])
+    w_fus, bits_fus = dict(zip(_lib.WEIGHT_FIELDS, outs[:-1])), outs[-1]
+    for k in _lib.WEIGHT_FIELDS:
+        np.testing.assert_allclose(w_fus[k].detach().cpu().numpy(), w_ref[k].detach().cpu().numpy(), rtol=1e-6, atol=1e-7,
+                                   err_msg=k)
+    np.testing.assert_allclose(bits_fus.detach().cpu().numpy(), bits_ref.detach().cpu().numpy(), rtol=2e-5)
+    # backward with random cotangents
+    cot = {k: torch.randn(w_ref[k].shape, device="cuda", generator=g) for k in _lib.WEIGHT_FIELDS}
+    cb = torch.rand(7, device="cuda", generator=g) + 0.1
+    for w, bits in ((w_ref, bits_ref), (w_fus, bits_fus)):
+        (sum((w[k] * cot[k]).sum() for k in _lib.WEIGHT_FIELDS) + (bits * cb).sum()).backward()
+    for (kn, pr), (_, pf) in zip(ref.named_parameters(), fus.named_parameters()):
+        assert pr.grad is not None and pf.grad is not None, kn
+        a, b = pf.grad.cpu().numpy(), pr.grad.cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=1e-5 * max(1.0, float(np.abs(b).max())), err_msg=kn)
