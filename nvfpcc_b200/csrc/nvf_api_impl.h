@@ -90,10 +90,14 @@ struct Api {
     else l.template layer<1>(p);
   }
   // weight gradient + bias gradient (db = per-channel sum of the output gradient `c.g`)
+  // Runs on the auxiliary stream: weight gradients only feed the final reduction, not the dgrad chain.
   static void wgrad_bias(L& l, const WgradParams& p, const ChanSumParams& c) {
-    if (l.fast_wgrad(p, c)) return;
-    wgrad(l, p);
-    l.chansum(c, c.C);
+    l.side_begin();
+    if (!l.fast_wgrad(p, c)) {
+      wgrad(l, p);
+      l.chansum(c, c.C);
+    }
+    l.side_end();
   }
   static void wgrad(L& l, const WgradParams& p) {
     const bool c8 = p.CA % 8 == 0;
@@ -174,7 +178,9 @@ struct Api {
     if (cls1) {  // conv1_cls + sigmoid (:4733-4741, :4764)
       p = LayerParams{a3, cls1, packed + g.cls1, w.cls1_b, nullptr, nullptr, n, d.c2, 1, 16, 16, 16, 16, 1, ACT_SIGMOID, OP_CORR3};
       p.out2 = p1;
+      l.side_begin();   // auxiliary head: off the critical path
       layer(l, p);
+      l.side_end();
     }
     // up2: convT k5 s2 p0 + ReLU (:4712-4719, :4765)
     p = LayerParams{a3, a4, packed + g.up2, w.up2_b, nullptr, nullptr, n, d.c2, d.c3, 16, 16, 35, 36, 0, ACT_RELU, OP_CONVT};
@@ -186,6 +192,7 @@ struct Api {
     p = LayerParams{a5, out, packed + g.cls2, w.cls2_b, nullptr, nullptr, n, d.c3, 1, 32, 32, 32, 32, 1, ACT_SIGMOID, OP_CORR3};
     p.out2 = p2;
     layer(l, p);
+    l.join();
   }
 
   static int decode(L& l, const NvfDesc* desc, const NvfWeights* w, const float* latent, const int32_t* origins,
@@ -394,7 +401,7 @@ struct Api {
     layer(l, p);
     p = LayerParams{g2, g1, packed + g.d_up1, nullptr, tmp1, a1, n, d.c2, d.c1, 19, 20, 8, 8, 0, ACT_NONE, OP_CORR_S2};
     layer(l, p);
-    if (!l.fast_stem_bwd(d, *w, latent, n, x0, a0, g1, wg ? gw : nullptr, (flags & NVF_BWD_DLATENT) ? g_latent : nullptr)) {
+    if (!l.fast_stem_bwd(d, *w, latent, n, x0, a0, g1, gy0, wg ? gw : nullptr, (flags & NVF_BWD_DLATENT) ? g_latent : nullptr)) {
       // ---- conv0 ----
       if (wg) {
         WgradParams q{a0, g1, gw->conv0_w, n, d.c0, d.c1, 4, 4, 8, 8, 5, 2, 2};
@@ -421,6 +428,7 @@ struct Api {
         layer(l, p);
       }
     }
+    l.join();
     l.flush_reduce();
     return l.error();
   }

@@ -17,6 +17,18 @@ using namespace nvf;
 namespace {
 
 thread_local int g_last_cuda = 0;
+
+// One auxiliary non-blocking stream + a ring of timing-free events per device, created lazily:
+// independent kernels of one call (weight gradients vs. the data-gradient chain, the auxiliary
+// heads) are forked onto it and joined back before the call returns, also under stream capture.
+constexpr int kMaxDevices = 16, kEventRing = 64;
+struct SidePool {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[kEventRing] = {};
+  int next = 0;
+  bool ready = false;
+};
+SidePool g_side[kMaxDevices];
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
 
 template <class TS>
@@ -146,13 +158,48 @@ __global__ void __launch_bounds__(kThreads) k_ffma(int variant, long long iters,
 
 // ------------------------------------------------------------------ launcher
 struct DevLauncher {
-  cudaStream_t st;
+  cudaStream_t st;      // stream kernels are launched on (the caller's stream, or the side stream inside a fork)
   int n_sms = 0;
   int rc = NVF_OK;
+  cudaStream_t main_st = nullptr;
+  SidePool* pool = nullptr;
+  bool forked = false;
+
+  // ---- fork / join of independent work onto the auxiliary stream
+  cudaEvent_t next_event() {
+    cudaEvent_t e = pool->ev[pool->next];
+    pool->next = (pool->next + 1) % kEventRing;
+    return e;
+  }
+  void side_begin() {   // subsequent launches run on the side stream, after everything launched so far
+    if (!pool || !pool->ready) return;
+    cudaEvent_t e = next_event();
+    if (!chk(cudaEventRecord(e, main_st)) || !chk(cudaStreamWaitEvent(pool->stream, e, 0))) return;
+    st = pool->stream;
+    forked = true;
+  }
+  void side_end() { st = main_st; }
+  void join() {         // the caller's stream waits for all forked work
+    if (!forked) return;
+    cudaEvent_t e = next_event();
+    if (chk(cudaEventRecord(e, pool->stream))) chk(cudaStreamWaitEvent(main_st, e, 0));
+    forked = false;
+  }
 
   int init() {
     int dev = 0, major = 0;
+    main_st = st;
     if (!chk(cudaGetDevice(&dev))) return rc;
+    if (dev >= 0 && dev < kMaxDevices) {
+      SidePool& P = g_side[dev];
+      if (!P.ready) {
+        bool ok = cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; ok && i < kEventRing; ++i) ok = cudaEventCreateWithFlags(&P.ev[i], cudaEventDisableTiming) == cudaSuccess;
+        P.ready = ok;
+        if (!ok) cudaGetLastError();   // run without forking
+      }
+      pool = &P;
+    }
     if (!chk(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev))) return rc;
     if (!chk(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev))) return rc;
     if (major != 10) rc = NVF_ERR_NO_DEVICE;
@@ -430,16 +477,23 @@ struct DevLauncher {
                      const float* cls0_wp, const float* latent, int n, float* x0, float* a0, float* a1, float* cls0,
                      float* cls0_copy) {
     if (n <= 0 || d.c1 % 8 || d.c0 > 32) return false;
-    const int smem = (d.ch * 8 + 2 * d.c0 * 64 + d.c1 * 512) * (int)sizeof(float);
-    if (!smem_attr(fast::k_stem_fwd, smem)) return true;
+    const int smem = (d.ch * 8 + 2 * d.c0 * 64) * (int)sizeof(float);
     fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
-                          cls0 ? cls0_wp : nullptr, w.cls0_b, x0, a0, a1, cls0, cls0_copy, n, d.ch, d.c0, d.c1};
-    fast::k_stem_fwd<<<n, fast::kStemThreads, smem, st>>>(q);
+                          nullptr, nullptr, x0, a0, a1, nullptr, nullptr, n, d.ch, d.c0, d.c1};
+    fast::k_stem_fwd<<<n * 8, 256, smem, st>>>(q);
     post();
+    if (cls0) {   // conv0_cls + sigmoid: auxiliary head, off the critical path
+      LayerParams p{a1, cls0, cls0_wp, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
+      p.out2 = cls0_copy;
+      side_begin();
+      const bool ok = fast_layer(p);
+      side_end();
+      if (!ok) k_generic<LayerKernel<1>><<<(n * 128 + kThreads - 1) / kThreads, kThreads, 0, st>>>(p), post();
+    }
     return true;
   }
   bool fast_stem_bwd(const NvfDesc& d, const NvfWeights& w, const float* latent, int n, const float* x0,
-                     const float* a0, const float* g1, const NvfWeightGrads* gw, float* g_latent) {
+                     const float* a0, const float* g1, float* gy0, const NvfWeightGrads* gw, float* g_latent) {
     if (n <= 0 || d.c1 % 8 || d.c0 > 32) return false;
     const int pf = fast::stem_partial_floats(d.ch, d.c0, d.c1);
     float* partial = nullptr;
@@ -447,11 +501,14 @@ struct DevLauncher {
       partial = take_partial((size_t)n * pf);
       if (!partial) return false;
     }
-    const int smem = (d.c1 * 512 + 9 * d.c0 * 64 + d.ch * 8) * (int)sizeof(float);
-    if (!smem_attr(fast::k_stem_bwd, smem)) return true;
+    const int smem_a = (d.c1 * 512 + 64 + 256) * (int)sizeof(float);
+    const int smem_b = (4 * d.c0 * 64 + d.ch * 8) * (int)sizeof(float);
+    if (!smem_attr(fast::k_stem_bwd_a, smem_a)) return true;
     fast::StemBwdParams q{latent, x0, a0, g1, w.igdn_beta, w.igdn_gamma, w.conv0_w, w.up0_w, partial, g_latent,
                           n, d.ch, d.c0, d.c1, gw ? 1 : 0};
-    fast::k_stem_bwd<<<n, fast::kStemThreads, smem, st>>>(q);
+    fast::k_stem_bwd_a<<<n * d.c0, 256, smem_a, st>>>(q, gy0);
+    post();
+    fast::k_stem_bwd_b<<<n, 256, smem_b, st>>>(q, gy0);
     post();
     if (gw) {
       const int n0 = d.c0 * d.c1 * 125, ng = d.c0 * d.c0, nu = d.ch * d.c0 * 125;

@@ -62,7 +62,10 @@ struct EmuLauncher {
   bool fast_stem_fwd(const NvfDesc&, const NvfWeights&, const float*, const float*, const float*, const float*, int,
                      float*, float*, float*, float*, float*) { return false; }
   bool fast_stem_bwd(const NvfDesc&, const NvfWeights&, const float*, int, const float*, const float*, const float*,
-                     const NvfWeightGrads*, float*) { return false; }
+                     float*, const NvfWeightGrads*, float*) { return false; }
+  void side_begin() {}
+  void side_end() {}
+  void join() {}
   void set_partial(float*, size_t) {}
   void flush_reduce() {}
   template <int COT>
