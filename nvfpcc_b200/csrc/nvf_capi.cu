@@ -429,13 +429,11 @@ struct DevLauncher {
     }
     return true;
   }
-  template <int C, int D, int TYB>
+  template <int C, int D, int TYB, int ZSEG>
   bool cls_wgrad(const WgradParams& p, float* db) {
-    using G = fast::ClsWgradCfg<C, D, TYB>;
-    auto* k = fast::k_cls_wgrad<C, D, TYB>;
-    const int items = p.n * D * G::BANDS;
-    int grid = n_sms * 2;
-    if (grid > items) grid = items;
+    using G = fast::ClsWgradCfg<C, D, TYB, ZSEG>;
+    auto* k = fast::k_cls_wgrad<C, D, TYB, ZSEG>;
+    const int grid = p.n * G::BANDS * G::SEGS;
     float* partial = take_partial((size_t)grid * G::OUT_FLOATS);
     if (!partial) return false;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
@@ -463,11 +461,11 @@ struct DevLauncher {
       return false;
     }
     if (p.K == 3 && p.S == 1 && p.P == 1 && p.CA == 1) {
-      if (p.CS == 8 && p.Da == 32) return cls_wgrad<8, 32, 8>(p, c.out);
-      if (p.CS == 8 && p.Da == 16) return cls_wgrad<8, 16, 8>(p, c.out);
-      if (p.CS == 16 && p.Da == 8) return cls_wgrad<16, 8, 8>(p, c.out);
-      if (p.CS == 16 && p.Da == 32) return cls_wgrad<16, 32, 8>(p, c.out);
-      if (p.CS == 16 && p.Da == 16) return cls_wgrad<16, 16, 8>(p, c.out);
+      if (p.CS == 8 && p.Da == 32) return cls_wgrad<8, 32, 16, 4>(p, c.out);
+      if (p.CS == 8 && p.Da == 16) return cls_wgrad<8, 16, 16, 4>(p, c.out);
+      if (p.CS == 16 && p.Da == 8) return cls_wgrad<16, 8, 8, 4>(p, c.out);
+      if (p.CS == 16 && p.Da == 32) return cls_wgrad<16, 32, 16, 4>(p, c.out);
+      if (p.CS == 16 && p.Da == 16) return cls_wgrad<16, 16, 16, 4>(p, c.out);
       return false;
     }
     return false;
@@ -477,7 +475,10 @@ struct DevLauncher {
                      const float* cls0_wp, const float* latent, int n, float* x0, float* a0, float* a1, float* cls0,
                      float* cls0_copy) {
     if (n <= 0 || d.c1 % 8 || d.c0 > 32) return false;
-    const int smem = (d.ch * 8 + 2 * d.c0 * 64) * (int)sizeof(float);
+    const int smem = (d.ch * 8 + 2 * d.c0 * 64 + d.c0 * d.c0 + d.c0 + ((d.ch * 125 * d.c0 + 3) & ~3) + d.c0 * 75 * d.c1) *
+                     (int)sizeof(float);
+    if (smem > 200 * 1024) return false;
+    if (!smem_attr(fast::k_stem_fwd, smem)) return true;
     fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
                           nullptr, nullptr, x0, a0, a1, nullptr, nullptr, n, d.ch, d.c0, d.c1};
     fast::k_stem_fwd<<<n * 8, 256, smem, st>>>(q);
@@ -501,9 +502,10 @@ struct DevLauncher {
       partial = take_partial((size_t)n * pf);
       if (!partial) return false;
     }
-    const int smem_a = (d.c1 * 512 + 64 + 256) * (int)sizeof(float);
-    const int smem_b = (4 * d.c0 * 64 + d.ch * 8) * (int)sizeof(float);
-    if (!smem_attr(fast::k_stem_bwd_a, smem_a)) return true;
+    const int smem_a = (d.c1 * 512 + 64 + 256 + d.c1 * 125) * (int)sizeof(float);
+    const int smem_b = (4 * d.c0 * 64 + d.ch * 8 + d.c0 * d.c0 + d.c0 + d.ch * d.c0 * 125) * (int)sizeof(float);
+    if (smem_a > 200 * 1024 || smem_b > 200 * 1024) return false;
+    if (!smem_attr(fast::k_stem_bwd_a, smem_a) || !smem_attr(fast::k_stem_bwd_b, smem_b)) return true;
     fast::StemBwdParams q{latent, x0, a0, g1, w.igdn_beta, w.igdn_gamma, w.conv0_w, w.up0_w, partial, g_latent,
                           n, d.ch, d.c0, d.c1, gw ? 1 : 0};
     fast::k_stem_bwd_a<<<n * d.c0, 256, smem_a, st>>>(q, gy0);

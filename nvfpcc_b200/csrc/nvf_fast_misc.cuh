@@ -18,13 +18,16 @@ struct ClsWgradParams {
   int32_t n;
 };
 
-template <int C, int D, int TYB>
+// One CTA = (block, row band, z segment): it streams along z with a ring of three staged
+// input slices (each slice is fetched once per CTA instead of three times).
+template <int C, int D, int TYB, int ZSEG>
 struct ClsWgradCfg {
   static constexpr int SETT = C * 9;
   static constexpr int NSET = 256 / SETT;
   static constexpr int PI = D + 4;                 // tile col c <-> ix = c - 1
   static constexpr int RA = TYB + 2;
-  static constexpr int A_FLOATS = C * 3 * RA * PI;
+  static constexpr int SLOT = C * RA * PI;         // one staged slice
+  static constexpr int A_FLOATS = 3 * SLOT;
   static constexpr int G_FLOATS = TYB * D;
   static constexpr int NW = C * 27;
   static constexpr int OUT_FLOATS = NW + 1;
@@ -32,12 +35,13 @@ struct ClsWgradCfg {
   static constexpr int SMEM_FLOATS = (A_FLOATS + G_FLOATS) > RED_FLOATS ? (A_FLOATS + G_FLOATS) : RED_FLOATS;
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
   static constexpr int BANDS = D / TYB;
-  static_assert(SETT <= 256 && D % 8 == 0 && D % TYB == 0, "cls wgrad tiling");
+  static constexpr int SEGS = D / ZSEG;
+  static_assert(SETT <= 256 && D % 8 == 0 && D % TYB == 0 && D % ZSEG == 0, "cls wgrad tiling");
 };
 
-template <int C, int D, int TYB>
+template <int C, int D, int TYB, int ZSEG>
 __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
-  using G = ClsWgradCfg<C, D, TYB>;
+  using G = ClsWgradCfg<C, D, TYB, ZSEG>;
   extern __shared__ __align__(16) float smem[];
   float* s_a = smem;
   float* s_g = smem + G::A_FLOATS;
@@ -51,31 +55,43 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
   float acc[3] = {0.f, 0.f, 0.f};
   float dbacc = 0.f;
 
-  const int items = p.n * D * G::BANDS;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    int q = item;
-    const int band = q % G::BANDS; q /= G::BANDS;
-    const int z = q % D; q /= D;
-    const int b = q;
-    const int y0 = band * TYB;
-    __syncthreads();
+  int q = blockIdx.x;
+  const int seg = q % G::SEGS; q /= G::SEGS;
+  const int band = q % G::BANDS; q /= G::BANDS;
+  const int b = q;
+  const int y0 = band * TYB, z0 = seg * ZSEG;
+  const float* ab = p.a + (size_t)b * C * D * D * D;
+
+  // stage input slice iz into ring slot (iz + 3) % 3 (zero outside the block: padding 1)
+  auto stage = [&](int iz) {
+    float* dst = s_a + ((iz + 3) % 3) * G::SLOT;
+    constexpr int NV = D / 4;
+    for (int i = tid; i < C * G::RA * NV; i += 256) {
+      int t = i;
+      const int xv = t % NV; t /= NV;
+      const int rr = t % G::RA; t /= G::RA;
+      const int ch = t;
+      const int iy = y0 + rr - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iz >= 0 && iz < D && iy >= 0 && iy < D)
+        v = __ldg(reinterpret_cast<const float4*>(ab + (((size_t)ch * D + iz) * D + iy) * D) + xv);
+      float* d = dst + (ch * G::RA + rr) * G::PI + 1 + 4 * xv;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  };
+  // the two halo columns of every staged row stay zero for the whole kernel
+  for (int i = tid; i < 3 * C * G::RA; i += 256) {
+    s_a[i * G::PI] = 0.f;
+    s_a[i * G::PI + D + 1] = 0.f;
+  }
+  stage(z0 - 1);
+  stage(z0);
+  for (int z = z0; z < z0 + ZSEG; ++z) {
+    stage(z + 1);
     {
       const float* gb = p.g + (((size_t)b * D + z) * D + y0) * D;
       for (int i = tid; i < G::G_FLOATS / 4; i += 256)
         reinterpret_cast<float4*>(s_g)[i] = __ldg(reinterpret_cast<const float4*>(gb) + i);
-      const float* ab = p.a + (size_t)b * C * D * D * D;
-      for (int i = tid; i < C * 3 * G::RA * G::PI; i += 256) {
-        int t = i;
-        const int c = t % G::PI; t /= G::PI;
-        const int rr = t % G::RA; t /= G::RA;
-        const int s = t % 3; t /= 3;
-        const int ch = t;
-        const int ix = c - 1, iy = y0 + rr - 1, iz = z + s - 1;
-        float v = 0.f;
-        if (ix >= 0 && ix < D && iy >= 0 && iy < D && iz >= 0 && iz < D)
-          v = __ldg(ab + (((size_t)ch * D + iz) * D + iy) * D + ix);
-        s_a[i] = v;
-      }
     }
     __syncthreads();
     {
@@ -84,11 +100,11 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
       dbacc += s;
     }
     if (active) {
-      const float* ab = s_a + ((ci * 3 + kz) * G::RA + ky) * G::PI;
+      const float* a_base = s_a + ((z + kz - 1 + 3) % 3) * G::SLOT + (ci * G::RA + ky) * G::PI;
       for (int rr = set; rr < TYB; rr += G::NSET) {
 #pragma unroll
         for (int xo = 0; xo < D / 8; ++xo) {
-          const float* ar = ab + rr * G::PI + 8 * xo;
+          const float* ar = a_base + rr * G::PI + 8 * xo;
           const float4 a0 = *reinterpret_cast<const float4*>(ar);
           const float4 a1 = *reinterpret_cast<const float4*>(ar + 4);
           const float2 a2 = *reinterpret_cast<const float2*>(ar + 8);
@@ -103,8 +119,8 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
         }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   float* red = smem;
   if (active) {
 #pragma unroll

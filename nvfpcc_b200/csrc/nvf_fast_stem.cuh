@@ -45,8 +45,23 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
   float* s_lat = smem;                 // [CH][8]
   float* s_x0 = s_lat + CH * 8;        // [C0][64]
   float* s_a0 = s_x0 + C0 * 64;        // [C0][64]
+  float* s_gam = s_a0 + C0 * 64;       // [C0][C0] gamma, then [C0] beta
+  float* s_wu = s_gam + C0 * C0 + C0;  // up0 weights [CH][125][C0]
+  float* s_wc = s_wu + ((CH * 125 * C0 + 3) & ~3);  // conv0 weights of this slice's kz parity [C0][3][25][C1]
   const int b = blockIdx.x >> 3, zs = blockIdx.x & 7, tid = threadIdx.x;
+  const int pz = zs & 1, NT = pz ? 2 : 3;              // kz = pz + 2t
   if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
+  for (int i = tid; i < C0 * C0 + C0; i += 256) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
+  for (int i = tid; i < CH * 125 * C0; i += 256) s_wu[i] = __ldg(p.up0_wp + i);
+  {
+    const int tapv = 25 * C1 / 4;   // float4 per (ci, kz)
+    for (int i = tid; i < C0 * 3 * tapv; i += 256) {
+      const int v4 = i % tapv, t = (i / tapv) % 3, ci = i / (3 * tapv);
+      if (t < NT)
+        reinterpret_cast<float4*>(s_wc)[i] =
+            __ldg(reinterpret_cast<const float4*>(p.conv0_wp + ((size_t)(ci * 5 + pz + 2 * t) * 25) * C1) + v4);
+    }
+  }
   __syncthreads();
   // up0: CH x 2^3 -> C0 x 4^3
   for (int idx = tid; idx < C0 * 64; idx += 256) {
@@ -63,7 +78,7 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
             const int tx = x + 2 - kx;
             if (tx < 0 || tx >= 4) continue;
             v = fmaf(s_lat[ci * 8 + (tz >> 1) * 4 + (ty >> 1) * 2 + (tx >> 1)],
-                     __ldg(p.up0_wp + ((size_t)ci * 125 + kz * 25 + ky * 5 + kx) * C0 + co), v);
+                     s_wu[(ci * 125 + kz * 25 + ky * 5 + kx) * C0 + co], v);
           }
         }
       }
@@ -74,10 +89,10 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
   // IGDN
   for (int idx = tid; idx < C0 * 64; idx += 256) {
     const int c = idx >> 6, pos = idx & 63;
-    float nn = p.beta[c];
+    float nn = s_gam[C0 * C0 + c];
     for (int j = 0; j < C0; ++j) {
       const float xj = s_x0[j * 64 + pos];
-      nn = fmaf(p.gamma[c * C0 + j], xj * xj, nn);
+      nn = fmaf(s_gam[c * C0 + j], xj * xj, nn);
     }
     const float v = s_x0[idx] * sqrtf(nn);
     s_a0[idx] = v;
@@ -90,8 +105,8 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
     const int pos = item & 63, cg = item >> 6;
     const int z = zs, y = pos >> 3, x = pos & 7;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kz = z & 1; kz < 5; kz += 2) {
-      const int tz = z + 2 - kz;
+    for (int t = 0; t < NT; ++t) {
+      const int tz = z + 2 - (pz + 2 * t);
       if (tz < 0 || tz >= 8) continue;
       for (int ky = y & 1; ky < 5; ky += 2) {
         const int ty = y + 2 - ky;
@@ -100,10 +115,11 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
           const int tx = x + 2 - kx;
           if (tx < 0 || tx >= 8) continue;
           const int ipos = (tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1);
-          const float* wk = p.conv0_wp + (size_t)(kz * 25 + ky * 5 + kx) * C1 + cg * 4;
+          const float* wk = s_wc + (size_t)(t * 25 + ky * 5 + kx) * C1 + cg * 4;
+#pragma unroll 4
           for (int ci = 0; ci < C0; ++ci) {
             const float a = s_a0[ci * 64 + ipos];
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wk + (size_t)ci * 125 * C1));
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + (size_t)ci * 75 * C1);
             acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
             acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
           }
@@ -145,12 +161,14 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
   float* s_g1 = smem;                   // [C1][512]
   float* s_a0 = s_g1 + C1 * 512;        // [64]
   float* s_part = s_a0 + 64;            // [4][64]
+  float* s_w = s_part + 256;            // conv0 W[ci][C1][125]
   const int b = blockIdx.x / C0, ci = blockIdx.x % C0, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   {
     const float4* src = reinterpret_cast<const float4*>(p.g1 + (size_t)b * C1 * 512);
     for (int i = tid; i < C1 * 128; i += 256) reinterpret_cast<float4*>(s_g1)[i] = __ldg(src + i);
     if (tid < 64) s_a0[tid] = p.a0[((size_t)b * C0 + ci) * 64 + tid];
+    for (int i = tid; i < C1 * 125; i += 256) s_w[i] = __ldg(p.conv0_w + (size_t)ci * C1 * 125 + i);
   }
   __syncthreads();
   float* part = p.partial ? p.partial + (size_t)b * stem_partial_floats(CH, C0, C1) : nullptr;
@@ -195,7 +213,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
     const int iz = (e >> 4) & 3, iy = (e >> 2) & 3, ix = e & 3;
     float s = 0.f;
     for (int co = h * (C1 / 4); co < (h + 1) * (C1 / 4); ++co) {
-      const float* wk = p.conv0_w + ((size_t)ci * C1 + co) * 125;
+      const float* wk = s_w + co * 125;
       for (int kz = 0; kz < 5; ++kz) {
         const int oz = 2 * iz + kz - 2;
         if (oz < 0 || oz >= 8) continue;
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
           for (int kx = 0; kx < 5; ++kx) {
             const int ox = 2 * ix + kx - 2;
             if (ox < 0 || ox >= 8) continue;
-            s = fmaf(s_g1[co * 512 + oz * 64 + oy * 8 + ox], __ldg(wk + kz * 25 + ky * 5 + kx), s);
+            s = fmaf(s_g1[co * 512 + oz * 64 + oy * 8 + ox], wk[kz * 25 + ky * 5 + kx], s);
           }
         }
       }
@@ -227,6 +245,8 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   float* s_gx = s_gy + C0 * 64;         // [C0][64]  dL/d(up0 out)
   float* s_n = s_gx + C0 * 64;          // [C0][64]  IGDN norm
   float* s_lat = s_n + C0 * 64;         // [CH][8]
+  float* s_gam = s_lat + CH * 8;        // [C0][C0] gamma, then [C0] beta
+  float* s_wu = s_gam + C0 * C0 + C0;   // up0 W (CH, C0, 125)
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < C0 * 64; i += 256) {
@@ -234,16 +254,19 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
     s_gy[i] = gy_in[(size_t)b * C0 * 64 + i];
   }
   if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
+  for (int i = tid; i < C0 * C0 + C0; i += 256) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
+  if (p.g_latent)
+    for (int i = tid; i < CH * C0 * 125; i += 256) s_wu[i] = __ldg(p.up0_w + i);
   __syncthreads();
   float* part = p.partial ? p.partial + (size_t)b * stem_partial_floats(CH, C0, C1) : nullptr;
   const int o_c0b = C0 * C1 * 125, o_gam = o_c0b + C1, o_bet = o_gam + C0 * C0, o_u0w = o_bet + C0,
             o_u0b = o_u0w + CH * C0 * 125;
   for (int e = tid; e < C0 * 64; e += 256) {
     const int c = e >> 6, pos = e & 63;
-    float nn = p.beta[c];
+    float nn = s_gam[C0 * C0 + c];
     for (int j = 0; j < C0; ++j) {
       const float xj = s_x0[j * 64 + pos];
-      nn = fmaf(p.gamma[c * C0 + j], xj * xj, nn);
+      nn = fmaf(s_gam[c * C0 + j], xj * xj, nn);
     }
     s_n[e] = sqrtf(nn);
   }
@@ -253,7 +276,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
     const int k = e >> 6, pos = e & 63;
     float acc = 0.f;
     for (int i = 0; i < C0; ++i)
-      acc += s_gy[i * 64 + pos] * s_x0[i * 64 + pos] * p.gamma[i * C0 + k] / s_n[i * 64 + pos];
+      acc += s_gy[i * 64 + pos] * s_x0[i * 64 + pos] * s_gam[i * C0 + k] / s_n[i * 64 + pos];
     s_gx[e] = s_gy[e] * s_n[e] + s_x0[e] * acc;
   }
   if (p.need_w && part) {
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
         const int co = t / 125, k = t % 125;
         const int oz = 2 * iz + k / 25 - 2, oy = 2 * iy + (k / 5) % 5 - 2, ox = 2 * ix + k % 5 - 2;
         if (oz < 0 || oz >= 4 || oy < 0 || oy >= 4 || ox < 0 || ox >= 4) continue;
-        s = fmaf(s_gx[co * 64 + oz * 16 + oy * 4 + ox], __ldg(p.up0_w + ((size_t)ci * C0 + co) * 125 + k), s);
+        s = fmaf(s_gx[co * 64 + oz * 16 + oy * 4 + ox], s_wu[(ci * C0 + co) * 125 + k], s);
       }
       for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) p.g_latent[(size_t)b * CH * 8 + e] = s;
