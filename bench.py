@@ -82,48 +82,59 @@ def calibrate_threshold_bias(net, latents, thh, target_occ=0.021, sample=64):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML from a background thread every ~2 ms
+    (nvidia-smi -lms cannot resolve a timed region of a few tens of milliseconds)."""
 
     def __init__(self, gpu_index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-        self.idx = gpu_index
+        import threading
+        self.idx, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.nv is None:
+            return
+        import threading
+        self.rows, self._stop = [], threading.Event()
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self.nv is None or self._t is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if "Active" in v and "Not" not in v:
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        os.unlink(self.f.name)
+        self._stop.set()
+        self._t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        if self.rows:
+            bits = 0
+            for _, r, _ in self.rows:
+                bits |= r
+            out.update(sm_mhz=statistics.median(r[0] for r in self.rows), sm_max_mhz=self.sm_max,
+                       reasons=sorted(n for n, b in names.items() if bits & b), samples=len(self.rows),
+                       power_w_max=max(r[2] for r in self.rows))
         return out
 
 
@@ -208,7 +219,7 @@ class TrainWorkload:
         self.nb = nb
         self.net = make_net(args.chanstr, "cuda")
         from nvfpcc_b200 import trainer
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=HP["lr"], capturable=True)
+        self.opt = trainer.FusedAdam(self.net.parameters(), lr=HP["lr"])
         self.emb = torch.ones(nb, 3, 2, 2, 2, device="cuda")
         self.B = HP["batch"]
         self.ws = trainer.WeightStep(self.net, self.opt, self.B, self.n_total, HP["lmbda"], HP["w1"], HP["w2"],
@@ -257,6 +268,7 @@ class DecodeWorkload:
         calibrate_threshold_bias(self.net, torch.from_numpy(lat).cuda(), HP["thh"])
         self.n_local = hi - lo
         self.points = 0
+        self.kernel_events = []
 
     def step(self, i, host_inputs):
         from nvfpcc_b200 import dist as D
@@ -267,7 +279,8 @@ class DecodeWorkload:
                 c_host = c.cpu()
                 self.points = c_host.shape[0]
         else:
-            r = self.net.decode_points(self.lat_dev, self.org_dev, HP["thh"], return_host=False)
+            r = self.net.decode_points(self.lat_dev, self.org_dev, HP["thh"], return_host=False,
+                                       timing=self.kernel_events)
             self.points = r["coords"].shape[0]
         return r
 
@@ -404,10 +417,16 @@ def main():
     for i in range(3):
         dw.step(i, False)
     dl0 = binding.launch_count()
-
+    dw.kernel_events = []
+    dsampler = ClockSampler(local)
+    if rank == 0:
+        dsampler.start()
     dms_total = timed(lambda i: dw.step(i, False), args.decode_steps, world, pre=lambda: flush_l2(flush))
+    dclocks = dsampler.stop() if rank == 0 else None
     dlaunches = binding.launch_count() - dl0
     dms = dms_total / args.decode_steps
+    # the nvf_decode launch sequence alone (k_decode_fused_A is 99.7 % of it, profiles/): CUDA events on its stream
+    dkernel_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in dw.kernel_events) / max(1, len(dw.kernel_events)), world)
     dec_value = dw.n_all * 32768 / (dms * 1e-3)
     for i in range(2):
         dw.step(i, True)
@@ -425,7 +444,7 @@ def main():
     peak = min(FP32_PEAK_THEORETICAL, max(peaks.values()))
     cs = args.chanstr
     t_ach = train_value / world * F_TRAIN[cs] / 1e12
-    d_ach = dec_value / world / 32768 * F_DEC[cs] / 1e12
+    d_ach = dw.n_local * F_DEC[cs] / (dkernel_ms * 1e-3) / 1e12   # rank 0's blocks / its kernel time
     line = dict(
         metric="train_blocks_per_sec", value=train_value, unit="blocks/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -440,6 +459,7 @@ def main():
                                   % (peaks["ffma"], peaks["ffma2"]),
                       kernel="whole train step (layer-wise kernels)"),
         decode=dict(metric="decoded_voxels_per_sec", value=dec_value, unit="voxels/s", ms_per_step=dms,
+                    ms_kernel=dkernel_ms, clocks=dclocks,
                     blocks=dw.n_all, points=int(dw.points), gpu_launches=int(dlaunches), steps=args.decode_steps,
                     workload="decode of all %d synthetic vox%d leaf blocks, thh %.2f, chanstr %s, calibrated ~2.1%% occupancy"
                              % (dw.n_all, 10 if args.resolution == 1024 else 11, HP["thh"], cs),
@@ -447,6 +467,7 @@ def main():
                              h2d_bytes_per_step=int(dw.n_all * (96 + 12)), d2h_bytes_per_step=int(dw.points * 12)),
                     roofline=dict(bound="fp32", achieved=d_ach, peak=peak, unit="TFLOP/s", frac=d_ach / peak,
                                   traffic=None, per_gpu=True, algorithmic_flop_per_block=F_DEC[cs],
+                                  timing="CUDA events around the nvf_decode launch sequence (pack + fused kernel + scan + emit)",
                                   kernel="k_decode_fused_A" if cs == "8,16,8,8" else "layer-wise kernels")),
     )
     if not args.skip_cpu_baseline and world == 1:

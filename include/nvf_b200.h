@@ -210,6 +210,59 @@ int nvf_param_prep_backward(const NvfDesc* desc, const NvfParamSet* params, floa
                             const NvfWeights* g_eff, const float* g_net_bits, const NvfParamGrads* out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Latent head, fused (forward + backward).  Replaces SingleLayerLatentGen.forward
+ * (utils/network.py:4610-4612: 1x1x1 IConv3d + GDN3d, gdn_3d.py:78-92) followed by
+ * QuantGaussianLikelihood.forward (utils/network.py:4514-4539: straight-through round,
+ * rate of the noisy (train) / rounded (eval) latent under N(mu_c, |sigma_c|), floor 1e-8).
+ *   ch        latent channels, 1..4
+ *   emb       [n, ch, 2,2,2]
+ *   noise     [n, ch, 2,2,2] U(0,1) samples or NULL; the rate argument in train mode is
+ *             y + (noise - 0.5) * noise_scale   (:4516-4525)
+ *   latent_out [n, ch, 2,2,2] rounded latent (decoder input); bits_out [1] summed rate in bits
+ *   workspace NVF_LATENT_WS_BYTES, zero-filled once by the caller; calls leave it zeroed where it matters
+ * Backward: g_latent = dLoss/d(latent_out) or NULL, g_bits [1] = dLoss/d(bits_out) (device scalar);
+ *   `grads` (all six pointers) or NULL, g_emb [n,ch,2,2,2] or NULL.
+ */
+#define NVF_LATENT_WS_BYTES (128 * 1024)
+typedef struct NvfLatentParams {
+  const float* kernel; const float* kernel_init;  /* latent_gen.h_analysis_2 (ch,ch,1,1,1) */
+  const float* b; const float* b_init;            /* (ch) */
+  const float* gdn_beta; const float* gdn_gamma;  /* latent_gen.gdn_2 raw (ch), (ch,ch) */
+  const float* sigma; const float* mu;            /* entropy_coder (1,ch,1,1,1) */
+} NvfLatentParams;
+typedef struct NvfLatentGrads {
+  float* kernel; float* b; float* gdn_beta; float* gdn_gamma; float* sigma; float* mu;
+} NvfLatentGrads;
+int nvf_latent_forward(int ch, const NvfLatentParams* params, const float* emb, const float* noise, float noise_scale,
+                       int train, int64_t n_blocks, float beta_bound, float gamma_bound, float pedestal,
+                       float* latent_out, float* bits_out, void* workspace, size_t workspace_bytes, void* stream);
+int nvf_latent_backward(int ch, const NvfLatentParams* params, const float* emb, const float* noise,
+                        float noise_scale, int train, int64_t n_blocks, float beta_bound, float gamma_bound,
+                        float pedestal, const float* g_latent, const float* g_bits, const NvfLatentGrads* grads,
+                        float* g_emb, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Total rate-distortion loss and the scalars train() logs (NVFPCC.py:161-164,190-221,196):
+ *   loss = bce + ms0 + ms1 + lmbda * (w1 * latent_bits / n_pts + w2 * sum(net_bits) / n_total)
+ *   sums        the NVF_LOSS_SUMS doubles of nvf_loss_seeds ([0] bce, [1] ms0, [2] ms1)
+ *   n_pts       [1] device scalar: occupied voxels of the (global) batch (NVFPCC.py:154)
+ *   loss_out [1]; stats_out [7] or NULL: loss bce ms0 ms1 b_latent b_net n_pts
+ * Backward: g_loss [1] -> g_dist [3] (bce, ms0, ms1), g_latent_bits [1], g_net_bits [NVF_NUM_QUANT].
+ */
+int nvf_rd_total(const double* sums, const float* latent_bits, const float* net_bits, const float* n_pts,
+                 float n_total, float lmbda, float w1, float w2, float* loss_out, float* stats_out, void* stream);
+int nvf_rd_total_backward(const float* g_loss, const float* n_pts, float n_total, float lmbda, float w1, float w2,
+                          float* g_dist, float* g_latent_bits, float* g_net_bits, void* stream);
+
+/*
+ * One Adam update of a flat parameter buffer (torch.optim.Adam defaults as used by train(),
+ * NVFPCC.py:116,124,222,250): no weight decay, no amsgrad.  `step` [1] float device counter
+ * (incremented by the call), `lr` [1] device scalar (so captured graphs follow LR schedules).
+ */
+int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* step,
+                  const float* lr, float beta1, float beta2, float eps, void* stream);
+
 /* FP32 FFMA throughput micro-benchmark (roofline denominator):
  * runs `iters` dependent-chain FFMA batches on every SM; returns the number of
  * FLOPs executed in flops_out.  The caller times it with CUDA events. */

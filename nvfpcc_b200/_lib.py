@@ -32,7 +32,11 @@ EXPORTS = (
     "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_launch_count", "nvf_has_fused_decode", "nvf_workspace_bytes",
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
     "nvf_ffma_microbench", "nvf_param_prep", "nvf_param_prep_backward",
+    "nvf_latent_forward", "nvf_latent_backward", "nvf_rd_total", "nvf_rd_total_backward", "nvf_adam_step",
 )
+LATENT_FIELDS = ("kernel", "kernel_init", "b", "b_init", "gdn_beta", "gdn_gamma", "sigma", "mu")   # NvfLatentParams
+LATENT_GRAD_FIELDS = ("kernel", "b", "gdn_beta", "gdn_gamma", "sigma", "mu")                         # NvfLatentGrads
+NVF_LATENT_WS_BYTES = 128 * 1024
 CONV_LAYERS = ("up0", "conv0", "up1", "conv1", "up2", "conv2", "cls2", "cls1", "cls0")   # NvfParamSet order
 NVF_NUM_CONV, NVF_NUM_QUANT, NVF_PARAM_WS_BYTES = 9, 7, 64 * 1024
 
@@ -69,6 +73,14 @@ class NvfParamSet(C.Structure):
 class NvfParamGrads(C.Structure):
     _fields_ = [("kernel", C.c_void_p * 9), ("b", C.c_void_p * 9), ("igdn_beta", C.c_void_p),
                 ("igdn_gamma", C.c_void_p), ("lik_sigma", C.c_void_p), ("lik_mu", C.c_void_p)]
+
+
+class NvfLatentParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in LATENT_FIELDS]
+
+
+class NvfLatentGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in LATENT_GRAD_FIELDS]
 
 
 class NvfError(RuntimeError):
@@ -111,6 +123,14 @@ class Binding:
                                      C.c_float, C.POINTER(NvfWeightGrads), vp, vp, C.c_size_t, vp]
         L.nvf_param_prep_backward.argtypes = [C.POINTER(NvfDesc), C.POINTER(NvfParamSet), C.c_float, C.c_float,
                                               C.POINTER(NvfWeights), vp, C.POINTER(NvfParamGrads), vp, C.c_size_t, vp]
+        f32 = C.c_float
+        L.nvf_latent_forward.argtypes = [C.c_int, C.POINTER(NvfLatentParams), vp, vp, f32, C.c_int, C.c_int64, f32, f32,
+                                         f32, vp, vp, vp, C.c_size_t, vp]
+        L.nvf_latent_backward.argtypes = [C.c_int, C.POINTER(NvfLatentParams), vp, vp, f32, C.c_int, C.c_int64, f32,
+                                          f32, f32, vp, vp, C.POINTER(NvfLatentGrads), vp, vp, C.c_size_t, vp]
+        L.nvf_rd_total.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
+        L.nvf_rd_total_backward.argtypes = [vp, vp, f32, f32, f32, f32, vp, vp, vp, vp]
+        L.nvf_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, f32, f32, f32, vp]
         if L.nvf_abi_version() != 1:
             raise NvfError("ABI version mismatch in %s" % path)
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -167,7 +187,9 @@ class Binding:
     # ------------------------------------------------------------------ calls
     def decode(self, desc: NvfDesc, weights: Dict[str, torch.Tensor], latent: torch.Tensor,
                origins: Optional[torch.Tensor], thh: float, want_prob: bool = False, want_coords: bool = True,
-               cap: Optional[int] = None):
+               cap: Optional[int] = None, timing: Optional[list] = None):
+        """timing: optional list; a (start, stop) pair of CUDA events recorded on the launching stream
+        immediately around the nvf_decode launch sequence is appended (bench.py roofline)."""
         dev = latent.device
         n = int(latent.shape[0])
         latent = latent.detach().contiguous().float()
@@ -183,9 +205,15 @@ class Binding:
         if cap is None:
             cap = n * 2048
         coords = torch.empty((cap, 3), dtype=torch.int32, device=dev) if want_coords else None
+        if timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rc = self.lib.nvf_decode(C.byref(desc), C.byref(wst), _ptr(latent), _ptr(origins), n, float(thh), _ptr(prob),
                                  _ptr(mask), _ptr(counts), _ptr(coords), cap if want_coords else 0, _ptr(total),
                                  _ptr(ws), nbytes, self._stream(dev))
+        if timing is not None:
+            ev[1].record()
+            timing.append(ev)
         self.check(rc, "nvf_decode")
         del keep
         res = dict(prob=prob, mask=mask, counts=counts, total=total, coords=None)
@@ -313,6 +341,100 @@ class Binding:
         self.check(rc, "nvf_param_prep_backward")
         del keep, keep2
         return out
+
+    # ---- fused latent head / total loss / Adam ----------------------------------------------------
+    def zeroed_workspace(self, nbytes: int, dev: torch.device, tag: str) -> torch.Tensor:
+        """Scratch that the library expects zero-filled on first use and leaves zeroed (ticket counters)."""
+        key = (str(dev), tag)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
+            self._ws[key] = buf
+        return buf
+
+    @staticmethod
+    def _latent_set(raw: Dict[str, torch.Tensor]):
+        ps, keep = NvfLatentParams(), []
+        for f in LATENT_FIELDS:
+            t = raw[f].detach().contiguous()
+            keep.append(t)
+            setattr(ps, f, t.data_ptr())
+        return ps, keep
+
+    def latent_forward(self, ch: int, raw: Dict[str, torch.Tensor], emb: torch.Tensor, noise: Optional[torch.Tensor],
+                       noise_scale: float, train: bool, bounds):
+        dev = emb.device
+        emb = emb.detach().contiguous().float()
+        n = int(emb.shape[0])
+        ps, keep = self._latent_set(raw)
+        latent = torch.empty_like(emb)
+        bits = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = self.zeroed_workspace(NVF_LATENT_WS_BYTES, dev, "latent")
+        rc = self.lib.nvf_latent_forward(int(ch), C.byref(ps), _ptr(emb), _ptr(noise), float(noise_scale), int(train), n,
+                                         float(bounds[0]), float(bounds[1]), float(bounds[2]), _ptr(latent), _ptr(bits),
+                                         _ptr(ws), ws.numel(), self._stream(dev))
+        self.check(rc, "nvf_latent_forward")
+        del keep
+        return latent, bits
+
+    def latent_backward(self, ch: int, raw: Dict[str, torch.Tensor], emb: torch.Tensor, noise: Optional[torch.Tensor],
+                        noise_scale: float, train: bool, bounds, g_latent: Optional[torch.Tensor],
+                        g_bits: torch.Tensor, want_params: bool, want_emb: bool,
+                        out: Optional[Dict[str, torch.Tensor]] = None):
+        """-> (grads dict over LATENT_GRAD_FIELDS or None, g_emb or None).  `out`: preallocated gradient tensors."""
+        dev = emb.device
+        emb = emb.detach().contiguous().float()
+        n = int(emb.shape[0])
+        ps, keep = self._latent_set(raw)
+        grads, gst = None, None
+        if want_params:
+            grads = out if out is not None else {f: torch.empty_like(raw[f], memory_format=torch.contiguous_format)
+                                                 for f in LATENT_GRAD_FIELDS}
+            gst = NvfLatentGrads()
+            for f in LATENT_GRAD_FIELDS:
+                setattr(gst, f, grads[f].data_ptr())
+        g_emb = torch.empty_like(emb) if want_emb else None
+        if g_latent is not None:
+            g_latent = g_latent.detach().contiguous().float()
+        g_bits = g_bits.detach().reshape(1).float()
+        ws = self.zeroed_workspace(NVF_LATENT_WS_BYTES, dev, "latent")
+        rc = self.lib.nvf_latent_backward(int(ch), C.byref(ps), _ptr(emb), _ptr(noise), float(noise_scale), int(train), n,
+                                          float(bounds[0]), float(bounds[1]), float(bounds[2]), _ptr(g_latent),
+                                          _ptr(g_bits), C.byref(gst) if gst is not None else None, _ptr(g_emb), _ptr(ws),
+                                          ws.numel(), self._stream(dev))
+        self.check(rc, "nvf_latent_backward")
+        del keep
+        return grads, g_emb
+
+    def rd_total(self, sums, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2, want_stats=True):
+        dev = sums.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        stats = torch.empty(7, dtype=torch.float32, device=dev) if want_stats else None
+        lb = latent_bits.detach().reshape(1).float()
+        nb = net_bits.detach().contiguous().float()
+        npts = n_pts.detach().reshape(1).float()
+        rc = self.lib.nvf_rd_total(_ptr(sums), _ptr(lb), _ptr(nb), _ptr(npts), float(n_total), float(lmbda), float(w1),
+                                   float(w2), _ptr(loss), _ptr(stats), self._stream(dev))
+        self.check(rc, "nvf_rd_total")
+        return loss, stats
+
+    def rd_total_backward(self, g_loss, n_pts, n_total, lmbda, w1, w2):
+        dev = g_loss.device
+        g_dist = torch.empty(3, dtype=torch.float32, device=dev)
+        g_lb = torch.empty(1, dtype=torch.float32, device=dev)
+        g_nb = torch.empty(NVF_NUM_QUANT, dtype=torch.float32, device=dev)
+        gl = g_loss.detach().reshape(1).float()
+        npts = n_pts.detach().reshape(1).float()
+        rc = self.lib.nvf_rd_total_backward(_ptr(gl), _ptr(npts), float(n_total), float(lmbda), float(w1), float(w2),
+                                            _ptr(g_dist), _ptr(g_lb), _ptr(g_nb), self._stream(dev))
+        self.check(rc, "nvf_rd_total_backward")
+        return g_dist, g_lb, g_nb
+
+    def adam_step(self, param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        rc = self.lib.nvf_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), int(param.numel()),
+                                    _ptr(step), _ptr(lr), float(beta1), float(beta2), float(eps),
+                                    self._stream(param.device))
+        self.check(rc, "nvf_adam_step")
 
     def launch_count(self) -> int:
         return int(self.lib.nvf_launch_count())

@@ -11,6 +11,7 @@
 #include "nvf_fast_misc.cuh"
 #include "nvf_fast_stem.cuh"
 #include "nvf_fast_params.cuh"
+#include "nvf_fast_latent.cuh"
 
 using namespace nvf;
 
@@ -712,6 +713,115 @@ int nvf_param_prep_backward(const NvfDesc* desc, const NvfParamSet* params, floa
   fast::k_param_prep<true><<<pp.total_chunks + 1, 256, 0, l.st>>>(pp);
   l.post();
   fast::k_param_final<true><<<1, 32, 0, l.st>>>(pp);
+  l.post();
+  return l.rc;
+}
+
+}  // extern "C"
+
+namespace {
+template <int CH>
+int latent_launch(DevLauncher& l, fast::LatentKParams& kp, bool bwd) {
+  int grid = (int)(((int64_t)kp.n * 8 + fast::kLatentThreads - 1) / fast::kLatentThreads);
+  if (grid > fast::kLatentMaxCtas) grid = fast::kLatentMaxCtas;
+  if (bwd) fast::k_latent_bwd<CH><<<grid, fast::kLatentThreads, 0, l.st>>>(kp);
+  else fast::k_latent_fwd<CH><<<grid, fast::kLatentThreads, 0, l.st>>>(kp);
+  l.post();
+  return l.rc;
+}
+int latent_call(int ch, const NvfLatentParams* ps, const float* emb, const float* noise, float noise_scale, int train,
+                int64_t n, float beta_bound, float gamma_bound, float pedestal, fast::LatentKParams& kp,
+                void* workspace, size_t workspace_bytes, void* stream, bool bwd) {
+  if (!ps || !emb || !workspace || n <= 0 || n > (1 << 24)) return NVF_ERR_INVALID_ARG;
+  if (!ps->kernel || !ps->kernel_init || !ps->b || !ps->b_init || !ps->gdn_beta || !ps->gdn_gamma || !ps->sigma || !ps->mu)
+    return NVF_ERR_INVALID_ARG;
+  if (ch < 1 || ch > 4) return NVF_ERR_UNSUPPORTED;
+  if (workspace_bytes < NVF_LATENT_WS_BYTES) return NVF_ERR_WORKSPACE;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  kp.emb = emb; kp.noise = noise;
+  kp.kernel = ps->kernel; kp.kernel_init = ps->kernel_init; kp.b = ps->b; kp.b_init = ps->b_init;
+  kp.beta = ps->gdn_beta; kp.gamma = ps->gdn_gamma; kp.sigma = ps->sigma; kp.mu = ps->mu;
+  kp.beta_bound = beta_bound; kp.gamma_bound = gamma_bound; kp.pedestal = pedestal; kp.noise_scale = noise_scale;
+  kp.n = (int32_t)n; kp.train = train ? 1 : 0;
+  kp.ticket = (unsigned int*)workspace;
+  kp.partial = (double*)((char*)workspace + 16);
+  switch (ch) {
+    case 1: return latent_launch<1>(l, kp, bwd);
+    case 2: return latent_launch<2>(l, kp, bwd);
+    case 3: return latent_launch<3>(l, kp, bwd);
+    default: return latent_launch<4>(l, kp, bwd);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int nvf_latent_forward(int ch, const NvfLatentParams* params, const float* emb, const float* noise, float noise_scale,
+                       int train, int64_t n_blocks, float beta_bound, float gamma_bound, float pedestal,
+                       float* latent_out, float* bits_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!latent_out || !bits_out) return NVF_ERR_INVALID_ARG;
+  fast::LatentKParams kp{};
+  kp.latent = latent_out; kp.bits_out = bits_out;
+  return latent_call(ch, params, emb, noise, noise_scale, train, n_blocks, beta_bound, gamma_bound, pedestal, kp,
+                     workspace, workspace_bytes, stream, false);
+}
+
+int nvf_latent_backward(int ch, const NvfLatentParams* params, const float* emb, const float* noise,
+                        float noise_scale, int train, int64_t n_blocks, float beta_bound, float gamma_bound,
+                        float pedestal, const float* g_latent, const float* g_bits, const NvfLatentGrads* grads,
+                        float* g_emb, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g_bits || (!grads && !g_emb)) return NVF_ERR_INVALID_ARG;
+  fast::LatentKParams kp{};
+  kp.g_latent = g_latent; kp.g_bits = g_bits; kp.g_emb = g_emb;
+  if (grads) {
+    if (!grads->kernel || !grads->b || !grads->gdn_beta || !grads->gdn_gamma || !grads->sigma || !grads->mu)
+      return NVF_ERR_INVALID_ARG;
+    kp.gk = grads->kernel; kp.gb = grads->b; kp.gbeta = grads->gdn_beta; kp.ggamma = grads->gdn_gamma;
+    kp.gsigma = grads->sigma; kp.gmu = grads->mu;
+  }
+  return latent_call(ch, params, emb, noise, noise_scale, train, n_blocks, beta_bound, gamma_bound, pedestal, kp,
+                     workspace, workspace_bytes, stream, true);
+}
+
+int nvf_rd_total(const double* sums, const float* latent_bits, const float* net_bits, const float* n_pts,
+                 float n_total, float lmbda, float w1, float w2, float* loss_out, float* stats_out, void* stream) {
+  if (!sums || !latent_bits || !net_bits || !n_pts || !loss_out) return NVF_ERR_INVALID_ARG;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::RdTotalParams p{};
+  p.sums = sums; p.latent_bits = latent_bits; p.net_bits = net_bits; p.n_pts = n_pts;
+  p.n_total = n_total; p.lmbda = lmbda; p.w1 = w1; p.w2 = w2;
+  p.loss = loss_out; p.stats = stats_out;
+  fast::k_rd_total<false><<<1, 32, 0, l.st>>>(p);
+  l.post();
+  return l.rc;
+}
+
+int nvf_rd_total_backward(const float* g_loss, const float* n_pts, float n_total, float lmbda, float w1, float w2,
+                          float* g_dist, float* g_latent_bits, float* g_net_bits, void* stream) {
+  if (!g_loss || !n_pts || !g_dist || !g_latent_bits || !g_net_bits) return NVF_ERR_INVALID_ARG;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::RdTotalParams p{};
+  p.g_loss = g_loss; p.n_pts = n_pts; p.n_total = n_total; p.lmbda = lmbda; p.w1 = w1; p.w2 = w2;
+  p.g_dist = g_dist; p.g_latent_bits = g_latent_bits; p.g_net_bits = g_net_bits;
+  fast::k_rd_total<true><<<1, 32, 0, l.st>>>(p);
+  l.post();
+  return l.rc;
+}
+
+int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* step,
+                  const float* lr, float beta1, float beta2, float eps, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || !lr || n <= 0) return NVF_ERR_INVALID_ARG;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::AdamParams p{param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, n};
+  int grid = (int)((n + 255) / 256);
+  if (grid > l.n_sms * 4) grid = l.n_sms * 4;
+  fast::k_adam<<<grid, 256, 0, l.st>>>(p);
+  l.post();
+  fast::k_adam_tick<<<1, 1, 0, l.st>>>(step);
   l.post();
   return l.rc;
 }

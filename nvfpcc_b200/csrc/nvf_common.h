@@ -60,6 +60,66 @@ NVF_HD void ld2(const float* p, float& a, float& b) {
 #endif
 }
 
+
+// ---------------------------------------------------------------------------
+// Packed pair of fp32 values living in one aligned 64-bit register pair, and the
+// Blackwell two-wide FMA (PTX fma.rn.f32x2 -> SASS FFMA2): each half is an IEEE
+// fmaf, so results are bit-identical to two scalar fmaf calls, but one warp
+// instruction feeds the FP32 pipe for two cycles - the issue slot freed every
+// other cycle is what the LDS / address instructions of the conv loops need.
+// On the host (CPU emulator) it is a plain struct.
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long p2;
+NVF_D p2 p2_make(float lo, float hi) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+NVF_D p2 p2_bcast(float a) { return p2_make(a, a); }
+NVF_D float p2_lo(p2 v) {
+  [[maybe_unused]] float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  (void)hi;
+  return lo;
+}
+NVF_D float p2_hi(p2 v) {
+  [[maybe_unused]] float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  (void)lo;
+  return hi;
+}
+// acc = a * b + acc (per half)
+NVF_D void p2_fma(p2& acc, p2 a, p2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+// four consecutive floats (16-byte aligned) -> pairs (p[0],p[1]) and (p[2],p[3]) with one 128-bit load
+NVF_D void p2_ld2(const float* p, p2& a, p2& b) {
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  a = v.x;
+  b = v.y;
+}
+#else
+struct p2 {
+  [[maybe_unused]] float lo, hi;
+};
+NVF_HD p2 p2_make(float lo, float hi) { return p2{lo, hi}; }
+NVF_HD p2 p2_bcast(float a) { return p2{a, a}; }
+NVF_HD float p2_lo(p2 v) { return v.lo; }
+NVF_HD float p2_hi(p2 v) { return v.hi; }
+NVF_HD void p2_fma(p2& acc, p2 a, p2 b) {
+  acc.lo = fmaf(a.lo, b.lo, acc.lo);
+  acc.hi = fmaf(a.hi, b.hi, acc.hi);
+}
+NVF_HD void p2_ld2(const float* p, p2& a, p2& b) {
+  a = p2{p[0], p[1]};
+  b = p2{p[2], p[3]};
+}
+#endif
+// eight consecutive output-channel weights -> four channel pairs
+NVF_HD void p2_load_w8(const float* wp, p2 (&w)[4]) {
+  p2_ld2(wp, w[0], w[1]);
+  p2_ld2(wp + 4, w[2], w[3]);
+}
+
 NVF_HD float relu(float v) { return v > 0.f ? v : 0.f; }
 // torch.sigmoid in fp32: 1/(1+exp(-x))
 NVF_HD float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }

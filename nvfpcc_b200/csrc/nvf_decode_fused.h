@@ -96,7 +96,7 @@ struct FusedAParams {
 
 // Per-thread state that lives across phases (registers on the GPU).
 struct FusedATS {
-  float acc[4][8][4];  // conv2 partial sums: [slot j: output slice z2-3+j][co][x]
+  p2 acc[4][4][4];     // conv2 partial sums: [slot j: output slice z2-3+j][co pair][x] (lo = even co)
   float cacc[3][4];    // cls partial sums:   [slot g: output slice z1-1+g][x]
   int cnt;             // points counted by this thread (mask flush lanes)
 };
@@ -134,11 +134,11 @@ struct FusedABlock {
     if (idx >= (cls == 0 ? 90 : 85)) return;
     const int yi = idx / 5, q = idx - yi * 5;
     const int y2 = 2 * yi + cls;
-    float acc[8][8];
+    p2 acc[4][8];  // [co pair][x]
     NVF_UNROLL
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       NVF_UNROLL
-      for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[c][j] = p2_bcast(0.f);
     }
     const float* W = sm + G::OFF_W_UP2;
     NVF_NOUNROLL
@@ -154,22 +154,22 @@ struct FusedABlock {
         for (int ky = cls; ky < 5; ky += 2) {
           const int row = ((y2 - ky) >> 1) + 2;  // y2-ky is even, >= -4
           const float* r = plane + row * G::IN_PITCH + 4 * q + 2;
-          float a[6];
-          ld2(r, a[0], a[1]);
+          float a0, a1;
+          ld2(r, a0, a1);
           f4 v = ld4(r + 2);
-          a[2] = v.x; a[3] = v.y; a[4] = v.z; a[5] = v.w;
+          const p2 a[6] = {p2_bcast(a0), p2_bcast(a1), p2_bcast(v.x), p2_bcast(v.y), p2_bcast(v.z), p2_bcast(v.w)};
           const float* wrow = W + (((ci * 5 + kz) * 5 + ky) * 5) * 8;
           NVF_UNROLL
           for (int kx = 0; kx < 5; ++kx) {
-            float w[8];
-            load_w<8>(wrow + kx * 8, w);
+            p2 w[4];
+            p2_load_w8(wrow + kx * 8, w);
             const int h = kx >> 1;
             NVF_UNROLL
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               NVF_UNROLL
               for (int j = 0; j < 4; ++j) {
-                if ((kx & 1) == 0) acc[c][2 * j] = fmaf(w[c], a[j + 2 - h], acc[c][2 * j]);
-                else acc[c][2 * j + 1] = fmaf(w[c], a[j + 2 - h], acc[c][2 * j + 1]);
+                if ((kx & 1) == 0) p2_fma(acc[c][2 * j], w[c], a[j + 2 - h]);
+                else p2_fma(acc[c][2 * j + 1], w[c], a[j + 2 - h]);
               }
             }
           }
@@ -181,8 +181,11 @@ struct FusedABlock {
     for (int c = 0; c < 8; ++c) {
       float* o = sm + G::OFF_U + c * G::U_PLANE + y2 * G::U_PITCH + 8 * q;
       const float bb = bias[c];
-      st4(o, relu(acc[c][0] + bb), relu(acc[c][1] + bb), relu(acc[c][2] + bb), relu(acc[c][3] + bb));
-      if (q < 4) st4(o + 4, relu(acc[c][4] + bb), relu(acc[c][5] + bb), relu(acc[c][6] + bb), relu(acc[c][7] + bb));
+      float v[8];
+      NVF_UNROLL
+      for (int j = 0; j < 8; ++j) v[j] = relu(((c & 1) ? p2_hi(acc[c >> 1][j]) : p2_lo(acc[c >> 1][j])) + bb);
+      st4(o, v[0], v[1], v[2], v[3]);
+      if (q < 4) st4(o + 4, v[4], v[5], v[6], v[7]);
     }
   }
 
@@ -196,7 +199,8 @@ struct FusedABlock {
       for (int ky = 0; ky < 4; ++ky) {
         const float* r = sm + G::OFF_U + ci * G::U_PLANE + (y + ky) * G::U_PITCH + x0;
         const f4 v0 = ld4(r), v1 = ld4(r + 4);
-        const float a[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const p2 a[8] = {p2_bcast(v0.x), p2_bcast(v0.y), p2_bcast(v0.z), p2_bcast(v0.w),
+                         p2_bcast(v1.x), p2_bcast(v1.y), p2_bcast(v1.z), p2_bcast(v1.w)};
         NVF_UNROLL
         for (int j = 0; j < 4; ++j) {
           if (!ALL && (j < lo || j > hi)) continue;
@@ -204,12 +208,12 @@ struct FusedABlock {
           const float* wrow = W + (((ci * 4 + kz) * 4 + ky) * 4) * 8;
           NVF_UNROLL
           for (int kx = 0; kx < 4; ++kx) {
-            float w[8];
-            load_w<8>(wrow + kx * 8, w);
+            p2 w[4];
+            p2_load_w8(wrow + kx * 8, w);
             NVF_UNROLL
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               NVF_UNROLL
-              for (int i = 0; i < 4; ++i) ts.acc[j][c][i] = fmaf(w[c], a[i + kx], ts.acc[j][c][i]);
+              for (int i = 0; i < 4; ++i) p2_fma(ts.acc[j][c][i], w[c], a[i + kx]);
             }
           }
         }
@@ -229,18 +233,20 @@ struct FusedABlock {
       NVF_UNROLL
       for (int c = 0; c < 8; ++c) {
         const float bb = bias[c];
-        st4(sm + G::OFF_C + c * G::C_PLANE + (y + 1) * G::C_PITCH + 4 + x0, relu(ts.acc[0][c][0] + bb),
-            relu(ts.acc[0][c][1] + bb), relu(ts.acc[0][c][2] + bb), relu(ts.acc[0][c][3] + bb));
+        float v[4];
+        NVF_UNROLL
+        for (int i = 0; i < 4; ++i) v[i] = relu(((c & 1) ? p2_hi(ts.acc[0][c >> 1][i]) : p2_lo(ts.acc[0][c >> 1][i])) + bb);
+        st4(sm + G::OFF_C + c * G::C_PLANE + (y + 1) * G::C_PITCH + 4 + x0, v[0], v[1], v[2], v[3]);
       }
     }
     NVF_UNROLL
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       NVF_UNROLL
       for (int i = 0; i < 4; ++i) {
         ts.acc[0][c][i] = ts.acc[1][c][i];
         ts.acc[1][c][i] = ts.acc[2][c][i];
         ts.acc[2][c][i] = ts.acc[3][c][i];
-        ts.acc[3][c][i] = 0.f;
+        ts.acc[3][c][i] = p2_bcast(0.f);
       }
     }
   }
@@ -422,9 +428,9 @@ struct FusedABlock {
         NVF_UNROLL
         for (int j = 0; j < 4; ++j) {
           NVF_UNROLL
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             NVF_UNROLL
-            for (int i = 0; i < 4; ++i) ts.acc[j][c][i] = 0.f;
+            for (int i = 0; i < 4; ++i) ts.acc[j][c][i] = p2_bcast(0.f);
           }
         }
         NVF_UNROLL

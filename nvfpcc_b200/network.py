@@ -344,9 +344,9 @@ class CompDecoder(nn.Module):
         return r["prob"]
 
     @torch.no_grad()
-    def decode_points(self, x, origins, thh, q=2, return_prob=False, return_host=None):
+    def decode_points(self, x, origins, thh, q=2, return_prob=False, return_host=None, timing=None):
         return ops.decode_blocks(self.in_channels, self.channels, self.effective_weights(q, aux=False), x, origins,
-                                 thh, return_prob=return_prob, return_host=return_host)
+                                 thh, return_prob=return_prob, return_host=return_host, timing=timing)
 
     def get_bits(self):
         aux_bits = sum(self.channels[i] * 2 for i in (1, 2, 3)) * 32 + 32 + (self.channels[1] ** 2 + self.channels[1]) * 32
@@ -363,9 +363,24 @@ class Net(nn.Module):
         self.entropy_coder = QuantGaussianLikelihood(in_channels=ch)
         self.reconstructor = CompDecoder(args, param_model, useIGDN=True, in_channels=ch, channels=channels)
 
+    def latent_raw(self) -> Dict[str, torch.Tensor]:
+        """The tensors the fused latent-head kernels read (_lib.LATENT_FIELDS)."""
+        h, g, e = self.latent_gen.h_analysis_2, self.latent_gen.gdn_2, self.entropy_coder
+        return dict(kernel=h.kernel, kernel_init=h.kernel_init, b=h.b, b_init=h.b_init, gdn_beta=g.beta,
+                    gdn_gamma=g.gamma, sigma=e.sigma, mu=e.mu)
+
+    def latent_head(self, emb, mode):
+        """latent_gen -> entropy_coder: (rounded latent, summed rate).  One fused kernel on the GPU."""
+        ch = self.reconstructor.in_channels
+        if emb.is_cuda and ch <= 4:
+            g = self.latent_gen.gdn_2
+            noise = torch.rand_like(emb)                       # drawn in both modes, like the reference (:4516)
+            return ops.latent_head(ch, emb, self.latent_raw(), mode, noise, self.entropy_coder.noise_scale,
+                                   g.beta_bound, g.gamma_bound, float(g.reparam_pedestal))
+        return self.entropy_coder(self.latent_gen(emb), mode)
+
     def forward(self, emb, mode, q):
-        latent = self.latent_gen(emb)
-        latent_rounded, latent_likelihood = self.entropy_coder(latent, mode)
+        latent_rounded, latent_likelihood = self.latent_head(emb, mode)
         out, out_cls_list, net_bits = self.reconstructor(latent_rounded, q)
         return out, out_cls_list, net_bits, latent_likelihood
 

@@ -34,7 +34,7 @@ def _to_dev(t: Optional[torch.Tensor], dev: torch.device, dtype=None):
 
 def decode_blocks(ch: int, channels: Sequence[int], weights: Dict[str, torch.Tensor], latents: torch.Tensor,
                   origins: Optional[torch.Tensor], thh: float, return_prob: bool = False,
-                  return_host: Optional[bool] = None):
+                  return_host: Optional[bool] = None, timing: Optional[list] = None):
     """latents [N,ch,2,2,2] (rounded), origins [N,3] -> dict(coords int32 [K,3], counts int32 [N], prob?).
 
     Inputs may live on the host (ideally pinned) or on the device; host inputs are
@@ -47,7 +47,7 @@ def decode_blocks(ch: int, channels: Sequence[int], weights: Dict[str, torch.Ten
         return_host = host_in
     w = {k: _to_dev(v, dev, torch.float32) for k, v in weights.items()}
     r = b.decode(b.desc(ch, channels), w, _to_dev(latents, dev, torch.float32),
-                 _to_dev(origins, dev, torch.int32), thh, want_prob=return_prob)
+                 _to_dev(origins, dev, torch.int32), thh, want_prob=return_prob, timing=timing)
     out = dict(coords=r["coords"], counts=r["counts"], prob=r["prob"], mask=r["mask"])
     if return_host:
         out = {k: (None if v is None else v.cpu()) for k, v in out.items()}
@@ -119,6 +119,82 @@ def rd_distortion(out, cls1, cls0, gt, dist, alpha_main: float = 0.9, alpha_aux:
     ms0/ms1 = get_focal_dense on the 8^3 / 16^3 heads against max-pooled GT (NVFPCC.py:166-184);
     sums: see include/nvf_b200.h (sse/denom at thh_metric, tp/ap/tn/an of each head at 0.5)."""
     return _RdDistortionFn.apply(out, cls1, cls0, gt, dist, float(alpha_main), float(alpha_aux), float(thh_metric))
+
+
+class _LatentHeadFn(torch.autograd.Function):
+    """forward: nvf_latent_forward; backward: nvf_latent_backward.  Inputs after the python
+    arguments: emb, then the 8 raw tensors in _lib.LATENT_FIELDS order."""
+
+    @staticmethod
+    def forward(ctx, ch, train, noise_scale, bounds, noise, emb, *raw):
+        b = _lib.cuda_binding()
+        if emb.device.type != "cuda":
+            raise NvfError("latent_head needs CUDA tensors; there is no CPU fallback")
+        rawd = dict(zip(_lib.LATENT_FIELDS, raw))
+        latent, bits = b.latent_forward(ch, rawd, emb, noise, noise_scale, train, bounds)
+        ctx.args = (ch, train, noise_scale, bounds)
+        ctx.noise = noise
+        ctx.save_for_backward(emb, *raw)
+        return latent, bits.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_latent, g_bits):
+        b = _lib.cuda_binding()
+        emb, *raw = ctx.saved_tensors
+        rawd = dict(zip(_lib.LATENT_FIELDS, raw))
+        ch, train, noise_scale, bounds = ctx.args
+        want_emb = ctx.needs_input_grad[5]
+        want_params = any(ctx.needs_input_grad[6:])
+        if g_bits is None:
+            g_bits = torch.zeros(1, device=emb.device)
+        grads, g_emb = b.latent_backward(ch, rawd, emb, ctx.noise, noise_scale, train, bounds, g_latent, g_bits,
+                                         want_params, want_emb)
+        ctx.noise = None
+        out = []
+        for i, f in enumerate(_lib.LATENT_FIELDS):
+            g = None
+            if grads is not None and f in grads and ctx.needs_input_grad[6 + i]:
+                g = grads[f].view_as(raw[i])
+            out.append(g)
+        return (None, None, None, None, None, g_emb) + tuple(out)
+
+
+def latent_head(ch: int, emb: torch.Tensor, raw: Dict[str, torch.Tensor], mode: str, noise: Optional[torch.Tensor],
+                noise_scale: float, beta_bound: float, gamma_bound: float, pedestal: float):
+    """Fused SingleLayerLatentGen + QuantGaussianLikelihood (see include/nvf_b200.h nvf_latent_forward):
+    emb [N,ch,2,2,2] -> (rounded latent [N,ch,2,2,2], summed rate in bits); differentiable w.r.t. emb and the
+    six trainable tensors.  raw: dict over _lib.LATENT_FIELDS; noise: U(0,1) samples shaped like emb or None."""
+    return _LatentHeadFn.apply(int(ch), mode == "train", float(noise_scale),
+                               (float(beta_bound), float(gamma_bound), float(pedestal)), noise, emb,
+                               *[raw[k] for k in _lib.LATENT_FIELDS])
+
+
+class _RdTotalFn(torch.autograd.Function):
+    """loss = bce + ms0 + ms1 + lmbda (w1 latent_bits / n_pts + w2 sum(net_bits) / n_total) in one launch
+    (NVFPCC.py:161-164,196); backward in one launch."""
+
+    @staticmethod
+    def forward(ctx, sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2):
+        b = _lib.cuda_binding()
+        loss, stats = b.rd_total(sums, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2)
+        ctx.consts = (n_total, lmbda, w1, w2)
+        ctx.save_for_backward(n_pts)
+        ctx.mark_non_differentiable(stats)
+        return loss.reshape(()), stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        b = _lib.cuda_binding()
+        (n_pts,) = ctx.saved_tensors
+        g_dist, g_lb, g_nb = b.rd_total_backward(g_loss, n_pts, *ctx.consts)
+        return None, g_dist[0], g_dist[1], g_dist[2], g_lb.reshape(()), g_nb, None, None, None, None, None
+
+
+def rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total: float, lmbda: float, w1: float, w2: float):
+    """-> (loss, stats[7] = loss bce ms0 ms1 b_latent b_net n_pts).  `sums`/`bce`/`ms0`/`ms1` as returned by
+    rd_distortion (the three scalars only carry the autograd edges; values are read from `sums`)."""
+    return _RdTotalFn.apply(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, float(n_total), float(lmbda),
+                            float(w1), float(w2))
 
 
 RAW_FIELDS = tuple("%s_%s" % (l, f) for l in _lib.CONV_LAYERS for f in ("kernel", "kernel_init", "b", "b_init")) + (

@@ -33,12 +33,72 @@ def _loss_terms(net, emb, gt, dst, q, n_total, lmbda, w1, w2, focal_alpha, n_pts
         n_pts = D.allreduce_sum_(gt.sum())                       # batch-global (NVFPCC.py:154,161)
     out, cls_list, net_bits, latent_bits = net(emb, "train", q)
     bce, ms0, ms1, sums = ops.rd_distortion(out, cls_list[1], cls_list[0], gt, dst, focal_alpha, 0.85, 0.6)
-    b_latent = latent_bits.sum() / n_pts
-    b_net = net_bits.sum() / n_total
-    loss = bce + ms0 + ms1 + lmbda * (b_latent * w1 + b_net * w2)
-    stats = torch.stack([loss.detach(), bce.detach(), ms0.detach(), ms1.detach(), b_latent.detach(),
-                         b_net.detach(), n_pts.detach().float()])
+    # total loss + the logged scalars in one launch (forward) / one launch (backward)
+    loss, stats = ops.rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2)
     return loss, stats, sums
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (defaults of train(), NVFPCC.py:116,124: betas (0.9, 0.999), eps 1e-8, no weight decay,
+    no amsgrad) over ONE flat buffer: all parameters are re-pointed to views of `flat`, the moments are flat too,
+    and step() is a single kernel (nvf_adam_step) instead of ~70 launches.  Learning-rate schedulers work as
+    usual (they edit param_groups[0]['lr']); the value is mirrored to a device scalar by sync_lr() so that a
+    captured CUDA graph follows the schedule.  One param group."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam supports a single param group")
+        self.ps = [p for p in self.param_groups[0]["params"]]
+        dev = self.ps[0].device
+        if dev.type != "cuda":
+            raise ops.NvfError("FusedAdam needs CUDA parameters; there is no CPU fallback")
+        n = sum(p.numel() for p in self.ps)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        o = 0
+        with torch.no_grad():
+            for p in self.ps:
+                k = p.numel()
+                self.flat[o:o + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + k].view(p.shape)
+                o += k
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+
+    def sync_lr(self):
+        """Mirror param_groups[0]['lr'] to the device scalar (call outside graph capture)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self.lr_t.fill_(lr)
+            self._lr_host = lr
+
+    def gather_grads(self) -> torch.Tensor:
+        """p.grad of every parameter -> flat_grad (one concatenation); missing grads count as zero."""
+        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.ps]
+        torch.cat(parts, out=self.flat_grad)
+        return self.flat_grad
+
+    @torch.no_grad()
+    def step(self, closure=None, gathered: bool = False):
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        if not gathered:
+            self.gather_grads()
+        g = self.param_groups[0]
+        ops._lib.cuda_binding().adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_t,
+                                          self.lr_t, g["betas"][0], g["betas"][1], g["eps"])
+
+    def snapshot(self):
+        return [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_t)]
+
+    def restore(self, snap):
+        for t, s in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_t), snap):
+            t.copy_(s)
 
 
 class WeightStep:
@@ -63,17 +123,22 @@ class WeightStep:
         self.use_graph = use_graph
         self.launches_per_step = 0
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
-        if use_graph:
+        self.fused_opt = isinstance(opt, FusedAdam)
+        if use_graph and not self.fused_opt:
             for g in opt.param_groups:
                 if not g.get("capturable", False):
-                    raise ValueError("WeightStep(use_graph=True) needs an optimizer built with capturable=True")
+                    raise ValueError("WeightStep(use_graph=True) needs FusedAdam or an optimizer built with capturable=True")
 
     def _body(self, q: int):
         self.opt.zero_grad(set_to_none=True)
         loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q, **self.hp)
         loss.backward()
-        D.allreduce_grads_(self.net.parameters())                # ONE all-reduce of the shared weights
-        self.opt.step()
+        if self.fused_opt:
+            D.allreduce_sum_(self.opt.gather_grads())            # ONE all-reduce of the flat shared-weight gradient
+            self.opt.step(gathered=True)
+        else:
+            D.allreduce_grads_(self.net.parameters())
+            self.opt.step()
         self.stats.copy_(stats)
         self.sums.copy_(sums)
 
@@ -98,9 +163,15 @@ class WeightStep:
 
     def _snapshot(self):
         import copy
+        if self.fused_opt:
+            return self.opt.snapshot()
         return [p.detach().clone() for p in self.net.parameters()], copy.deepcopy(self.opt.state_dict())
 
     def _restore(self, state):
+        if self.fused_opt:
+            with torch.no_grad():
+                self.opt.restore(state)
+            return
         params, opt_sd = state
         with torch.no_grad():
             for p, s in zip(self.net.parameters(), params):
@@ -124,6 +195,8 @@ class WeightStep:
         if not self.use_graph:
             self._body(q)
             return self.stats
+        if self.fused_opt:
+            self.opt.sync_lr()
         if q not in self._graphs:
             self._capture(q)
         self._graphs[q].replay()

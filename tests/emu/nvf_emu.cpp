@@ -173,4 +173,19 @@ int nvf_param_prep(const NvfDesc*, const NvfParamSet*, int, const float*, float,
                    float*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
 int nvf_param_prep_backward(const NvfDesc*, const NvfParamSet*, float, float, const NvfWeights*, const float*,
                             const NvfParamGrads*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
+// likewise the latent head, total loss and Adam kernels
+int nvf_latent_forward(int, const NvfLatentParams*, const float*, const float*, float, int, int64_t, float, float, float,
+                       float*, float*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_latent_backward(int, const NvfLatentParams*, const float*, const float*, float, int, int64_t, float, float,
+                        float, const float*, const float*, const NvfLatentGrads*, float*, void*, size_t, void*) {
+  return NVF_ERR_UNSUPPORTED;
+}
+int nvf_rd_total(const double*, const float*, const float*, const float*, float, float, float, float, float*, float*,
+                 void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_rd_total_backward(const float*, const float*, float, float, float, float, float*, float*, float*, void*) {
+  return NVF_ERR_UNSUPPORTED;
+}
+int nvf_adam_step(float*, const float*, float*, float*, int64_t, float*, const float*, float, float, float, void*) {
+  return NVF_ERR_UNSUPPORTED;
+}
 }  // extern "C"

@@ -220,3 +220,127 @@ def test_fused_param_prep_matches_torch_path(gpu, q):
         assert pr.grad is not None and pf.grad is not None, kn
         a, b = pf.grad.cpu().numpy(), pr.grad.cpu().numpy()
         np.testing.assert_allclose(a, b, rtol=2e-4, atol=1e-5 * max(1.0, float(np.abs(b).max())), err_msg=kn)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_fused_latent_head_matches_torch_modules(gpu, mode):
+    """nvf_latent_forward/backward against the torch modules they replace (SingleLayerLatentGen + GDN3d,
+    utils/network.py:4610-4612, gdn_3d.py:78-92; QuantGaussianLikelihood, :4514-4539) incl. autograd, with a
+    perturbed state so that every LowerBound / abs branch carries signal."""
+    from nvfpcc_b200 import network, ops, synth
+    fx = fixture_inputs("A")
+    network.set_seed(synth.synthetic_seed())
+    nets = []
+    for _ in range(2):
+        network.seed_ptr = 0
+        n = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8")
+        n.load_state_dict(fx["sd"])
+        nets.append(n.cuda())
+    ref, fus = nets
+    with torch.no_grad():
+        for r in (ref, fus):
+            r.latent_gen.gdn_2.gamma[0, 1] = 1e-7      # below the bound: LowerBound branch
+            r.latent_gen.gdn_2.beta[2] = 1e-4
+            r.entropy_coder.sigma[0, 1] = -0.7         # abs() branch
+            r.entropy_coder.mu[0, 2] = 0.3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    emb_r = (torch.randn(37, 3, 2, 2, 2, device="cuda", generator=g) * 3).requires_grad_(True)
+    emb_f = emb_r.detach().clone().requires_grad_(True)
+    noise = torch.rand(37, 3, 2, 2, 2, device="cuda", generator=g)
+    # torch path with the same noise
+    x = ref.latent_gen(emb_r)
+    x_round = network.bypass_round(x)
+    x_form = x + (noise - 0.5) * 1.0 if mode == "train" else x_round
+    bits_r = ref.entropy_coder.gaussian_model(x_form, torch.abs(ref.entropy_coder.sigma), ref.entropy_coder.mu)
+    gd = fus.latent_gen.gdn_2
+    lat_f, bits_f = ops.latent_head(3, emb_f, fus.latent_raw(), mode, noise, 1.0, gd.beta_bound, gd.gamma_bound,
+                                    float(gd.reparam_pedestal))
+    assert torch.equal(lat_f, x_round.detach()) or (lat_f - x_round.detach()).abs().max() == 0
+    np.testing.assert_allclose(bits_f.item(), bits_r.item(), rtol=2e-5)
+    cot = torch.randn(37, 3, 2, 2, 2, device="cuda", generator=g)
+    ((x_round * cot).sum() + 0.37 * bits_r).backward()
+    ((lat_f * cot).sum() + 0.37 * bits_f).backward()
+    np.testing.assert_allclose(emb_f.grad.cpu().numpy(), emb_r.grad.cpu().numpy(), rtol=2e-4,
+                               atol=1e-5 * float(emb_r.grad.abs().max()))
+    names = ("latent_gen.h_analysis_2.kernel", "latent_gen.h_analysis_2.b", "latent_gen.gdn_2.beta",
+             "latent_gen.gdn_2.gamma", "entropy_coder.sigma", "entropy_coder.mu")
+    pr, pf = dict(ref.named_parameters()), dict(fus.named_parameters())
+    for k in names:
+        a, b = pf[k].grad.cpu().numpy(), pr[k].grad.cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=3e-4, atol=1e-5 * max(1.0, float(np.abs(b).max())), err_msg=k)
+
+
+def test_fused_latent_head_many_blocks_is_deterministic(gpu):
+    """More blocks than one CTA handles: the ticketed cross-CTA reduction gives identical bits run to run."""
+    from nvfpcc_b200 import network, ops, synth
+    network.set_seed(synth.synthetic_seed())
+    net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8").cuda()
+    emb = torch.randn(1247, 3, 2, 2, 2, device="cuda") * 2
+    noise = torch.rand_like(emb)
+    gd = net.latent_gen.gdn_2
+    outs = []
+    for _ in range(3):
+        e = emb.clone().requires_grad_(True)
+        lat, bits = ops.latent_head(3, e, net.latent_raw(), "train", noise, 1.0, gd.beta_bound, gd.gamma_bound,
+                                    float(gd.reparam_pedestal))
+        net.zero_grad()
+        (bits + lat.sum()).backward()
+        outs.append((bits.item(), e.grad.clone(), net.entropy_coder.mu.grad.clone()))
+    x = net.latent_gen(emb)
+    ref = net.entropy_coder.gaussian_model(x + (noise - 0.5), torch.abs(net.entropy_coder.sigma), net.entropy_coder.mu)
+    np.testing.assert_allclose(outs[0][0], ref.item(), rtol=2e-5)
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+
+
+def test_fused_adam_matches_torch_adam(gpu):
+    """trainer.FusedAdam (nvf_adam_step on one flat buffer) == torch.optim.Adam over several steps,
+    including a learning-rate change by a scheduler."""
+    from nvfpcc_b200 import trainer
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(3, 8, 5, 5, 5), (8,), (1, 3, 1, 1, 1), (16, 16), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, lr=1e-3)
+    ob = trainer.FusedAdam(pb, lr=1e-3)
+    sa = torch.optim.lr_scheduler.MultiStepLR(oa, [3], 0.01)
+    sb = torch.optim.lr_scheduler.MultiStepLR(ob, [3], 0.01)
+    for it in range(6):
+        grads = [torch.randn(s, device="cuda", generator=g) * (10.0 ** (it - 3)) for s in shapes]
+        for o, ps in ((oa, pa), (ob, pb)):
+            o.zero_grad()
+            for p, gr in zip(ps, grads):
+                p.grad = gr.clone()
+            o.step()
+        sa.step(), sb.step()
+        for a, b in zip(pa, pb):
+            np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+    assert ob.param_groups[0]["lr"] == oa.param_groups[0]["lr"] == pytest.approx(1e-5)
+
+
+def _make_fused_step(graph):
+    from nvfpcc_b200 import network, synth, trainer
+    network.set_seed(synth.synthetic_seed())
+    net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8").cuda()
+    net.entropy_coder.noise_scale = 0.0
+    opt = trainer.FusedAdam(net.parameters(), lr=1e-3)
+    return net, trainer.WeightStep(net, opt, batch=2, n_total=849338.0, lmbda=200.0, w1=10.0, w2=57.0, use_graph=graph)
+
+
+def test_fused_adam_weight_step_equals_torch_adam_step(gpu, golden_A):
+    """WeightStep with FusedAdam (graph replay) walks the same trajectory as the eager torch-Adam step."""
+    gt = torch.from_numpy(golden_A["tr_gt"]).float().cuda()
+    dist = torch.from_numpy(golden_A["tr_dist"]).float().cuda()
+    emb = torch.ones(2, 3, 2, 2, 2).cuda()
+    stats, params = {}, {}
+    for kind in ("torch", "fused"):
+        net, ws = _make_step(False) if kind == "torch" else _make_fused_step(True)
+        hist = []
+        for i in range(4):
+            hist.append(ws.step(emb, gt if i % 2 == 0 else gt.flip(0), dist if i % 2 == 0 else dist.flip(0), q=2).clone())
+        stats[kind] = torch.stack(hist).cpu()
+        params[kind] = [p.detach().cpu().clone() for p in net.parameters()]
+    np.testing.assert_allclose(stats["fused"].numpy(), stats["torch"].numpy(), rtol=1e-5, atol=1e-6)
+    for a, b in zip(params["fused"], params["torch"]):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=2e-6)
+    assert stats["fused"][2, 0] < stats["fused"][0, 0]
