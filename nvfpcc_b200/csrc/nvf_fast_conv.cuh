@@ -71,13 +71,22 @@ __global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC
   const int zp = r % NZP; r /= NZP;
   const int cg = r;
 
+  // accumulators: output-channel PAIRS in 64-bit registers (fma.rn.f32x2) when COT is even
+  constexpr bool PAIR = (COT % 2 == 0);
+  constexpr int CP = PAIR ? COT / 2 : COT;
+  p2 acc2[2][CP][4];
   float acc[2][COT][4];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[a][c][j] = p2_bcast(0.f);
 #pragma unroll
     for (int c = 0; c < COT; ++c)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[a][c][j] = 0.f;
+  }
 
   const float* in_b = p.in + (size_t)b * CI * DIN * DIN * G::IN_PITCH;
   constexpr int plane = DIN * G::IN_PITCH;
@@ -133,50 +142,95 @@ __global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC
         for (int ky = 0; ky < K; ++ky) {
           const float* rowp = s_in + ((ci * G::TZI + 2 * zp) * G::TYI + ty + ky) * G::PI + 4 * xg;
           const float* wp = s_w + ((ci * K) * K + ky) * K * C + cg * COT;
-          float a0[8], a1[8];
-          {
-            const float4 lo = *reinterpret_cast<const float4*>(rowp);
-            const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
-            a0[0] = lo.x; a0[1] = lo.y; a0[2] = lo.z; a0[3] = lo.w;
-            a0[4] = hi.x; a0[5] = hi.y; a0[6] = hi.z; a0[7] = hi.w;
-          }
-#pragma unroll
-          for (int kz = 0; kz < K; ++kz) {
+          if constexpr (PAIR) {
+            p2 a0[8], a1[8];
             {
-              const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
-              const float4 lo = *reinterpret_cast<const float4*>(r1);
-              const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
-              a1[0] = lo.x; a1[1] = lo.y; a1[2] = lo.z; a1[3] = lo.w;
-              a1[4] = hi.x; a1[5] = hi.y; a1[6] = hi.z; a1[7] = hi.w;
+              const float4 lo = *reinterpret_cast<const float4*>(rowp);
+              const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
+              a0[0] = p2_bcast(lo.x); a0[1] = p2_bcast(lo.y); a0[2] = p2_bcast(lo.z); a0[3] = p2_bcast(lo.w);
+              a0[4] = p2_bcast(hi.x); a0[5] = p2_bcast(hi.y); a0[6] = p2_bcast(hi.z); a0[7] = p2_bcast(hi.w);
             }
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-              const float* wk = wp + (kz * K * K + kx) * C;
-              float w[COT];
-              if (COT == 8) {
-                const float4 w0 = *reinterpret_cast<const float4*>(wk);
-                const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
-                w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
-                w[4 % COT] = w1.x; w[5 % COT] = w1.y; w[6 % COT] = w1.z; w[7 % COT] = w1.w;
-              } else {
-#pragma unroll
-                for (int c = 0; c < COT; ++c) w[c] = wk[c];
+            for (int kz = 0; kz < K; ++kz) {
+              {
+                const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
+                const float4 lo = *reinterpret_cast<const float4*>(r1);
+                const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
+                a1[0] = p2_bcast(lo.x); a1[1] = p2_bcast(lo.y); a1[2] = p2_bcast(lo.z); a1[3] = p2_bcast(lo.w);
+                a1[4] = p2_bcast(hi.x); a1[5] = p2_bcast(hi.y); a1[6] = p2_bcast(hi.z); a1[7] = p2_bcast(hi.w);
               }
 #pragma unroll
-              for (int c = 0; c < COT; ++c) {
+              for (int kx = 0; kx < K; ++kx) {
+                const float* wk = wp + (kz * K * K + kx) * C;
+                p2 w[CP];
+                if constexpr (COT == 8) {
+                  p2_ld2(wk, w[0], w[1]);
+                  p2_ld2(wk + 4, w[2 % CP], w[3 % CP]);
+                } else if constexpr (COT == 4) {
+                  p2_ld2(wk, w[0], w[1 % CP]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  acc[0][c][j] = fmaf(w[c], a0[j + kx], acc[0][c][j]);
-                  acc[1][c][j] = fmaf(w[c], a1[j + kx], acc[1][c][j]);
+                  for (int c = 0; c < CP; ++c) w[c] = p2_make(wk[2 * c], wk[2 * c + 1]);
+                }
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    p2_fma(acc2[0][c][j], w[c], a0[j + kx]);
+                    p2_fma(acc2[1][c][j], w[c], a1[j + kx]);
+                  }
                 }
               }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a0[i] = a1[i];
+            }
+          } else {
+            float a0[8], a1[8];
+            {
+              const float4 lo = *reinterpret_cast<const float4*>(rowp);
+              const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
+              a0[0] = lo.x; a0[1] = lo.y; a0[2] = lo.z; a0[3] = lo.w;
+              a0[4] = hi.x; a0[5] = hi.y; a0[6] = hi.z; a0[7] = hi.w;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a0[i] = a1[i];
+            for (int kz = 0; kz < K; ++kz) {
+              {
+                const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
+                const float4 lo = *reinterpret_cast<const float4*>(r1);
+                const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
+                a1[0] = lo.x; a1[1] = lo.y; a1[2] = lo.z; a1[3] = lo.w;
+                a1[4] = hi.x; a1[5] = hi.y; a1[6] = hi.z; a1[7] = hi.w;
+              }
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx) {
+                const float* wk = wp + (kz * K * K + kx) * C;
+                float w[COT];
+#pragma unroll
+                for (int c = 0; c < COT; ++c) w[c] = wk[c];
+#pragma unroll
+                for (int c = 0; c < COT; ++c) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    acc[0][c][j] = fmaf(w[c], a0[j + kx], acc[0][c][j]);
+                    acc[1][c][j] = fmaf(w[c], a1[j + kx], acc[1][c][j]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a0[i] = a1[i];
+            }
           }
         }
       }
     }
+  }
+  if constexpr (PAIR) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < COT; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][c][j] = (c & 1) ? p2_hi(acc2[a][c >> 1][j]) : p2_lo(acc2[a][c >> 1][j]);
   }
   if (!active) return;
   // ---- epilogue
@@ -273,13 +327,13 @@ __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
   const int ci = r % C; r /= C;
   const int cog = r;
 
-  float acc[8][2][4];
+  p2 acc2[4][2][4];   // [co pair][ky of the pair][kx]: lo = even co, hi = odd co (fma.rn.f32x2)
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int x = 0; x < 4; ++x) acc[c][k][x] = 0.f;
+      for (int x = 0; x < 4; ++x) acc2[c][k][x] = p2_bcast(0.f);
   float dbacc = 0.f;
   constexpr int DB_PARTS = 256 / C;  // threads per channel for the bias-gradient side sum
   const int db_c = tid / DB_PARTS, db_part = tid % DB_PARTS;
@@ -296,10 +350,13 @@ __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
     {
       constexpr int NVG = G::GP / 4;
       const float* gb = p.g + (((size_t)b * C) * DG + z) * DG * G::GP + (size_t)y0 * G::GP;
+      // s_g[c/2][row][x][c&1]: the two channels of a pair are interleaved so that one LDS.128 yields
+      // the (g_c, g_c+1) operand pairs of two x positions
       for (int i = tid; i < C * TYG * NVG; i += 256) {
         const int c = i / (TYG * NVG), rem = i - c * (TYG * NVG);
-        *reinterpret_cast<float4*>(s_g + c * TYG * G::GP + rem * 4) =
-            __ldg(reinterpret_cast<const float4*>(gb + (size_t)c * DG * DG * G::GP) + rem);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(gb + (size_t)c * DG * DG * G::GP) + rem);
+        float* d = s_g + ((c >> 1) * TYG * G::GP + rem * 4) * 2 + (c & 1);
+        d[0] = v.x; d[2] = v.y; d[4] = v.z; d[6] = v.w;
       }
       constexpr int NVA = G::APG / 4;
       constexpr int RA = TYG + 3;
@@ -317,43 +374,52 @@ __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
     __syncthreads();
     // ---- bias gradient side sum (all threads, C channels x DB_PARTS parts)
     {
-      const float* gc = s_g + db_c * TYG * G::GP;
+      const float* gc = s_g + (db_c >> 1) * TYG * G::GP * 2 + (db_c & 1);
       float s = 0.f;
-      for (int i = db_part; i < TYG * DG; i += DB_PARTS) s += gc[(i / DG) * G::GP + (i % DG)];
+      for (int i = db_part; i < TYG * DG; i += DB_PARTS) s += gc[((i / DG) * G::GP + (i % DG)) * 2];
       dbacc += s;
     }
     // ---- main accumulation
     const float* a_base = s_a + (ci * 4 + kz) * G::ZSA + (2 * kyp) * G::AP;
-    const float* g_base = s_g + (cog * 8) * TYG * G::GP;
+    const float* g_base = s_g + (cog * 4) * TYG * G::GP * 2;
 #pragma unroll 1
     for (int rr = 0; rr < G::ROWS_PER_SET; ++rr) {
       const int row = set * G::ROWS_PER_SET + rr;
 #pragma unroll 2
       for (int xq = 0; xq < G::XQ; ++xq) {
-        float av[2][8];
+        p2 av[2][8];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float* ar = a_base + (row + k) * G::AP + 4 * xq;
           const float4 lo = *reinterpret_cast<const float4*>(ar);
           const float4 hi = *reinterpret_cast<const float4*>(ar + 4);
-          av[k][0] = lo.x; av[k][1] = lo.y; av[k][2] = lo.z; av[k][3] = lo.w;
-          av[k][4] = hi.x; av[k][5] = hi.y; av[k][6] = hi.z; av[k][7] = hi.w;
+          av[k][0] = p2_bcast(lo.x); av[k][1] = p2_bcast(lo.y); av[k][2] = p2_bcast(lo.z); av[k][3] = p2_bcast(lo.w);
+          av[k][4] = p2_bcast(hi.x); av[k][5] = p2_bcast(hi.y); av[k][6] = p2_bcast(hi.z); av[k][7] = p2_bcast(hi.w);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 g4 = *reinterpret_cast<const float4*>(g_base + (c * TYG + row) * G::GP + 4 * xq);
-          const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        for (int c = 0; c < 4; ++c) {
+          p2 gv[4];
+          const float* gr = g_base + ((c * TYG + row) * G::GP + 4 * xq) * 2;
+          p2_ld2(gr, gv[0], gv[1]);
+          p2_ld2(gr + 4, gv[2], gv[3]);
 #pragma unroll
           for (int k = 0; k < 2; ++k)
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) acc[c][k][kx] = fmaf(gv[j], av[k][j + kx], acc[c][k][kx]);
+              for (int j = 0; j < 4; ++j) p2_fma(acc2[c][k][kx], gv[j], av[k][j + kx]);
         }
       }
     }
   }
   // ---- CTA result: sum the position sets, write one partial in PyTorch layout (co,ci,kz,ky,kx)
+  float acc[8][2][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[c][k][x] = (c & 1) ? p2_hi(acc2[c >> 1][k][x]) : p2_lo(acc2[c >> 1][k][x]);
   __syncthreads();
   float* out = p.partial + (size_t)blockIdx.x * G::OUT_FLOATS;
   if (G::NSET > 1) {

@@ -91,13 +91,13 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
   const int y = 4 * rg + sub;      // rows y and y + 2 (parity `sub`)
   const int NKY = sub ? 2 : 3;     // ky = sub + 2u, input rows 2rg - u (row y) and 2rg - u + 1 (row y + 2)
 
-  float acc[2][4][8];
+  p2 acc2[2][2][8];   // [row of the pair][co pair][x]: fma.rn.f32x2 over output-channel pairs
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[a][c][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc2[a][c][j] = p2_bcast(0.f);
 
 #pragma unroll 1
   for (int ci = 0; ci < CI; ++ci) {
@@ -105,12 +105,13 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
     for (int t = 0; t < NT; ++t) {
       // tile rows 2rg .. 2rg+3  (iy = 2rg-2 .. 2rg+1), columns 4q+2 .. 4q+7  (ix = 4q-2 .. 4q+3)
       const float* base = s_in + ((ci * 3 + t) * G::TR + 2 * rg) * G::IP + 4 * q + 2;
-      float R[4][6];
+      p2 R[4][6];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 lo = *reinterpret_cast<const float2*>(base + k * G::IP);
         const float4 hi = *reinterpret_cast<const float4*>(base + k * G::IP + 2);
-        R[k][0] = lo.x; R[k][1] = lo.y; R[k][2] = hi.x; R[k][3] = hi.y; R[k][4] = hi.z; R[k][5] = hi.w;
+        R[k][0] = p2_bcast(lo.x); R[k][1] = p2_bcast(lo.y); R[k][2] = p2_bcast(hi.x);
+        R[k][3] = p2_bcast(hi.y); R[k][4] = p2_bcast(hi.z); R[k][5] = p2_bcast(hi.w);
       }
       const float* wt = s_w + ((ci * 3 + t) * 25) * CO + cog * 4;
 #pragma unroll
@@ -119,19 +120,19 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
           const int ky = sub + 2 * u;
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + (ky * 5 + kx) * CO);
-            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            p2 w[2];
+            p2_ld2(wt + (ky * 5 + kx) * CO, w[0], w[1]);
             const int h = kx >> 1;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if ((kx & 1) == 0) {
-                  acc[0][c][2 * j] = fmaf(w[c], R[2 - u][j + 2 - h], acc[0][c][2 * j]);
-                  acc[1][c][2 * j] = fmaf(w[c], R[3 - u][j + 2 - h], acc[1][c][2 * j]);
+                  p2_fma(acc2[0][c][2 * j], w[c], R[2 - u][j + 2 - h]);
+                  p2_fma(acc2[1][c][2 * j], w[c], R[3 - u][j + 2 - h]);
                 } else {
-                  acc[0][c][2 * j + 1] = fmaf(w[c], R[2 - u][j + 2 - h], acc[0][c][2 * j + 1]);
-                  acc[1][c][2 * j + 1] = fmaf(w[c], R[3 - u][j + 2 - h], acc[1][c][2 * j + 1]);
+                  p2_fma(acc2[0][c][2 * j + 1], w[c], R[2 - u][j + 2 - h]);
+                  p2_fma(acc2[1][c][2 * j + 1], w[c], R[3 - u][j + 2 - h]);
                 }
               }
             }
@@ -140,6 +141,13 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
       }
     }
   }
+  float acc[2][4][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][c][j] = (c & 1) ? p2_hi(acc2[a][c >> 1][j]) : p2_lo(acc2[a][c >> 1][j]);
   // ---- epilogue: bias + ReLU, columns >= DOUT of a padded row are written as zero
   constexpr size_t out_cs = (size_t)G::DOUT * G::DOUT * G::OUT_PITCH;
 #pragma unroll
@@ -217,13 +225,13 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
   const int yp = r % G::NYP; r /= G::NYP;
   const int cxg = r;
 
-  float acc[2][8][4];
+  p2 acc2[2][4][4];   // [row][cx pair][x]: fma.rn.f32x2 over input-channel pairs
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[a][c][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc2[a][c][j] = p2_bcast(0.f);
 
   const float* g_b = p.g + (size_t)b * CG * G::DG * G::DG * G::GP;
   for (int c0 = 0; c0 < CG; c0 += CGC) {
@@ -249,33 +257,40 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
 #pragma unroll 1
         for (int ky = 0; ky < 5; ++ky) {
           const float* ra = s_g + ((c * 5 + kz) * G::GR + 4 * yp + ky) * G::GPS + 8 * xg;
-          float A[2][12];
+          p2 A[2][12];
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
               const float4 f = *reinterpret_cast<const float4*>(ra + a * 2 * G::GPS + 4 * v);
-              A[a][4 * v] = f.x; A[a][4 * v + 1] = f.y; A[a][4 * v + 2] = f.z; A[a][4 * v + 3] = f.w;
+              A[a][4 * v] = p2_bcast(f.x); A[a][4 * v + 1] = p2_bcast(f.y);
+              A[a][4 * v + 2] = p2_bcast(f.z); A[a][4 * v + 3] = p2_bcast(f.w);
             }
           }
           const float* wk = s_w + ((c * 5 + kz) * 5 + ky) * 5 * CX + cxg * 8;
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
-            const float4 w0 = *reinterpret_cast<const float4*>(wk + kx * CX);
-            const float4 w1 = *reinterpret_cast<const float4*>(wk + kx * CX + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            p2 w[4];
+            p2_load_w8(wk + kx * CX, w);
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc)
+            for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                acc[0][cc][j] = fmaf(w[cc], A[0][2 * j + kx], acc[0][cc][j]);
-                acc[1][cc][j] = fmaf(w[cc], A[1][2 * j + kx], acc[1][cc][j]);
+                p2_fma(acc2[0][cc][j], w[cc], A[0][2 * j + kx]);
+                p2_fma(acc2[1][cc][j], w[cc], A[1][2 * j + kx]);
               }
           }
         }
       }
     }
   }
+  float acc[2][8][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[a][c][j] = (c & 1) ? p2_hi(acc2[a][c >> 1][j]) : p2_lo(acc2[a][c >> 1][j]);
   // ---- combine the five kz groups (fixed order), add / mask, store
   __syncthreads();
   float* red = smem;
@@ -363,11 +378,12 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
   const int tt = active ? tid : 0;
   const int ky = tt % 5, kz = (tt / 5) % 5, co = tt / 25;
 
-  float acc[CIB][5];
+  static_assert(CIB % 2 == 0, "input channels are processed in pairs (fma.rn.f32x2)");
+  p2 acc2[CIB / 2][5];   // [ci pair][kx]
 #pragma unroll
-  for (int c = 0; c < CIB; ++c)
+  for (int c = 0; c < CIB / 2; ++c)
 #pragma unroll
-    for (int k = 0; k < 5; ++k) acc[c][k] = 0.f;
+    for (int k = 0; k < 5; ++k) acc2[c][k] = p2_bcast(0.f);
 
   const int items = p.n * DIN * G::BANDS;
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -396,8 +412,10 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
         const int cv = t % XV; t /= XV;
         const int rr = t % TYB; t /= TYB;
         const int c = t;
-        reinterpret_cast<float4*>(s_x)[i] =
-            __ldg(reinterpret_cast<const float4*>(xb + (((size_t)c * DIN + z) * DIN + y0 + rr) * DIN) + cv);
+        // s_x[c/2][rr][x][c&1]: channel pairs interleaved (one LDS.128 = the operand pairs of two x)
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)c * DIN + z) * DIN + y0 + rr) * DIN) + cv);
+        float* d = s_x + (((c >> 1) * TYB + rr) * DIN + 4 * cv) * 2 + (c & 1);
+        d[0] = v.x; d[2] = v.y; d[4] = v.z; d[6] = v.w;
       }
     }
     __syncthreads();
@@ -408,20 +426,23 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
 #pragma unroll 1
         for (int xq = 0; xq < DIN / 4; ++xq) {
           const float* gr = gk + 2 * rr * G::ROWP + 8 * xq;
-          float gv[12];
+          p2 gv[12];
 #pragma unroll
           for (int v = 0; v < 3; ++v) {
             const float4 f = *reinterpret_cast<const float4*>(gr + 4 * v);
-            gv[4 * v] = f.x; gv[4 * v + 1] = f.y; gv[4 * v + 2] = f.z; gv[4 * v + 3] = f.w;
+            gv[4 * v] = p2_bcast(f.x); gv[4 * v + 1] = p2_bcast(f.y);
+            gv[4 * v + 2] = p2_bcast(f.z); gv[4 * v + 3] = p2_bcast(f.w);
           }
 #pragma unroll
-          for (int c = 0; c < CIB; ++c) {
-            const float4 x4 = *reinterpret_cast<const float4*>(s_x + (c * TYB + rr) * DIN + 4 * xq);
-            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+          for (int c = 0; c < CIB / 2; ++c) {
+            p2 xv[4];
+            const float* xr = s_x + ((c * TYB + rr) * DIN + 4 * xq) * 2;
+            p2_ld2(xr, xv[0], xv[1]);
+            p2_ld2(xr + 4, xv[2], xv[3]);
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) acc[c][kx] = fmaf(xv[j], gv[2 * j + kx], acc[c][kx]);
+              for (int j = 0; j < 4; ++j) p2_fma(acc2[c][kx], xv[j], gv[2 * j + kx]);
           }
         }
       }
@@ -433,7 +454,8 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
 #pragma unroll
   for (int c = 0; c < CIB; ++c)
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) out[((c * 8 + co) * 25 + kz * 5 + ky) * 5 + kx] = acc[c][kx];
+    for (int kx = 0; kx < 5; ++kx)
+      out[((c * 8 + co) * 25 + kz * 5 + ky) * 5 + kx] = (c & 1) ? p2_hi(acc2[c >> 1][kx]) : p2_lo(acc2[c >> 1][kx]);
 }
 
 // ---------------------------------------------------------------------------
