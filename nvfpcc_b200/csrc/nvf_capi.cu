@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) k_pack(PackParams p) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_decode_fused_A(FusedAParams p) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   DevEnv<FusedATS> env;
   FusedABlock<DevEnv<FusedATS>>::run(env, p, smem, blockIdx.x, gridDim.x);
 }
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) k_generic(typename K::Params p) {
 
 template <int COT, int K>
 __global__ void __launch_bounds__(kThreads) k_wgrad(WgradParams p) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   DevEnv<int> env;
   WgradBlock<COT, K>::run(env, p, smem, blockIdx.x);
 }
@@ -292,14 +292,23 @@ struct DevLauncher {
     return chk(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
 
-  template <int K, int CI, int CO, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB>
+  template <int K, int CI, int CO, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA = false>
   bool conv_s1(const LayerParams& p) {
-    using G = fast::ConvS1Cfg<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC>;
-    static_assert(G::SMEM_BYTES <= 227 * 1024, "conv_s1 smem");
-    auto* k = fast::k_conv_s1<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, MINB>;
-    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    constexpr int XSH = TMA ? (4 - PAD % 4) % 4 : 0;
+    static_assert(XSH <= 1, "TMA tiles support PAD % 4 in {0, 3}");
+    using G = fast::ConvS1Cfg<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, XSH>;
+    constexpr int SMEM = TMA ? G::SMEM_BYTES_TMA : G::SMEM_BYTES;
+    static_assert(SMEM <= 227 * 1024, "conv_s1 smem");
+    auto* k = fast::k_conv_s1<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, MINB, TMA>;
+    if (!smem_attr(k, SMEM)) return true;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (TMA && !tma::make_map_5d(&map, p.in, p.n, CI, DIN, DIN, G::IN_PITCH, G::PI, G::TYI, G::TZI, CIC)) {
+      if (rc == NVF_OK) rc = NVF_ERR_CUDA;    // no silent fallback: the TMA path is the product path
+      return true;
+    }
     fast::ConvS1Params q{p.in, p.out, p.out2, p.Wp, p.bias, p.mask, p.n, p.act};
-    k<<<p.n * G::TILES_Z * G::TILES_Y, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    k<<<p.n * G::TILES_Z * G::TILES_Y, G::THREADS, SMEM, st>>>(map, q);
     post();
     return true;
   }
@@ -331,10 +340,10 @@ struct DevLauncher {
     if (p.op == OP_CORR4 && p.CI == p.CO && !p.add && !p.out2 && p.act != ACT_SIGMOID) {
       const bool fwd = p.P == 0 && !p.mask, dg = p.P == 3;
       if (p.CI == 8) {
-        if (fwd && p.Din == 35) return conv_s1<4, 8, 8, 35, 0, 8, 16, 2, 4, 2>(p);
-        if (dg && p.Din == 32) return conv_s1<4, 8, 8, 32, 3, 9, 12, 2, 4, 2>(p);
-        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 4, 4>(p);
-        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 4, 4>(p);
+        if (fwd && p.Din == 35) return conv_s1<4, 8, 8, 35, 0, 8, 16, 2, 2, 2, true>(p);
+        if (dg && p.Din == 32) return conv_s1<4, 8, 8, 32, 3, 9, 12, 2, 2, 2, true>(p);
+        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 2, 4, true>(p);
+        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 2, 4, true>(p);
       } else if (p.CI == 16) {
         if (fwd && p.Din == 35) return conv_s1<4, 16, 16, 35, 0, 8, 16, 1, 4, 2>(p);
         if (dg && p.Din == 32) return conv_s1<4, 16, 16, 32, 3, 9, 12, 1, 4, 2>(p);

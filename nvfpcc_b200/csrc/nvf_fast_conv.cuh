@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "nvf_common.h"
+#include "nvf_tma.cuh"
 
 namespace nvf {
 namespace fast {
@@ -29,7 +30,10 @@ struct ConvS1Params {
   int32_t n, act;     // act: 0 none, 1 relu, 2 sigmoid
 };
 
-template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC>
+// XSH: extra left shift of the staged columns (tile column = ix + PAD + XSH).  The TMA unit needs the
+// innermost start coordinate of a box to be 16-byte aligned (x0 = -(PAD + XSH) must be a multiple of 4:
+// probed on B200, scripts/probe/tma_probe.cu), so the PAD = 3 data-gradient tiles use XSH = 1.
+template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int XSH = 0>
 struct ConvS1Cfg {
   static constexpr int COT = C >= 8 ? 8 : C;               // output channels per thread
   static constexpr int DOUT = DIN + 2 * PAD - (K - 1);
@@ -40,21 +44,127 @@ struct ConvS1Cfg {
   static constexpr int THREADS = (THREADS_USED + 31) / 32 * 32;
   static constexpr int TZ = 2 * NZP;                      // output slices per tile
   static constexpr int TZI = TZ + K - 1, TYI = TY + K - 1;
-  static constexpr int PI = 4 * XG + 4;                   // input row pitch (x0 .. x0+7 readable)
+  static constexpr int PI = 4 * XG + 4 + (XSH ? 4 : 0);   // input row pitch (x0 .. x0+7(+XSH) readable)
   static constexpr int IN_FLOATS = CIC * TZI * TYI * PI;
   static constexpr int W_FLOATS = CIC * K * K * K * C;
   static constexpr int SMEM_BYTES = (IN_FLOATS + W_FLOATS) * 4;
+  // TMA variant: two stages of {input tile, weight chunk}, each part 128-byte aligned, + two mbarriers
+  static constexpr int IN_AL = (IN_FLOATS + 31) / 32 * 32, W_AL = (W_FLOATS + 31) / 32 * 32, STAGE = IN_AL + W_AL;
+  static constexpr int SMEM_BYTES_TMA = 2 * STAGE * 4 + 16;
   static constexpr int TILES_Z = (DOUT + TZ - 1) / TZ, TILES_Y = (DOUT + TY - 1) / TY;
   static_assert(C % COT == 0 && CI % CIC == 0 && (K == 3 || K == 4), "channel blocking");
   static_assert(4 * XG >= DOUT && 4 * XG <= OUT_PITCH, "x groups cover one output row");
   static_assert(PAD % 4 != 0 || 4 * NV <= PI, "staged row fits the tile pitch");
 };
+// One staged chunk of CIC input channels: accumulate into the thread's register tile.
+// s_in: [CIC][TZI][TYI][PI] input tile (halo included), s_w: [CIC][K][K][K][C] weights.
+// eight consecutive tile columns starting at r[XSH] (r 16-byte aligned) as broadcast pairs
+template <int XSH>
+__device__ __forceinline__ void load_row8_p2(const float* r, p2 (&a)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(r);
+  const float4 hi = *reinterpret_cast<const float4*>(r + 4);
+  if constexpr (XSH == 0) {
+    a[0] = p2_bcast(lo.x); a[1] = p2_bcast(lo.y); a[2] = p2_bcast(lo.z); a[3] = p2_bcast(lo.w);
+    a[4] = p2_bcast(hi.x); a[5] = p2_bcast(hi.y); a[6] = p2_bcast(hi.z); a[7] = p2_bcast(hi.w);
+  } else {
+    static_assert(XSH == 0 || XSH == 1, "XSH");
+    const float4 h2 = *reinterpret_cast<const float4*>(r + 8);
+    a[0] = p2_bcast(lo.y); a[1] = p2_bcast(lo.z); a[2] = p2_bcast(lo.w); a[3] = p2_bcast(hi.x);
+    a[4] = p2_bcast(hi.y); a[5] = p2_bcast(hi.z); a[6] = p2_bcast(hi.w); a[7] = p2_bcast(h2.x);
+  }
+}
 
-template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB>
-__global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC>::THREADS, MINB) k_conv_s1(ConvS1Params p) {
-  using G = ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC>;
+template <class G, int K, int C, int CIC, int COT, int CP, bool PAIR, int XSH>
+__device__ __forceinline__ void conv_s1_chunk(const float* __restrict__ s_in, const float* __restrict__ s_w, int zp, int ty,
+                                              int xg, int cg, p2 (&acc2)[2][CP][4], float (&acc)[2][COT][4]) {
+#pragma unroll 1
+  for (int ci = 0; ci < CIC; ++ci) {
+#pragma unroll 1
+    for (int ky = 0; ky < K; ++ky) {
+      const float* rowp = s_in + ((ci * G::TZI + 2 * zp) * G::TYI + ty + ky) * G::PI + 4 * xg;
+      const float* wp = s_w + ((ci * K) * K + ky) * K * C + cg * COT;
+      if constexpr (PAIR) {
+        p2 a0[8], a1[8];
+        load_row8_p2<XSH>(rowp, a0);
+#pragma unroll
+        for (int kz = 0; kz < K; ++kz) {
+          load_row8_p2<XSH>(rowp + (kz + 1) * G::TYI * G::PI, a1);
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float* wk = wp + (kz * K * K + kx) * C;
+            p2 w[CP];
+            if constexpr (COT == 8) {
+              p2_ld2(wk, w[0], w[1]);
+              p2_ld2(wk + 4, w[2 % CP], w[3 % CP]);
+            } else if constexpr (COT == 4) {
+              p2_ld2(wk, w[0], w[1 % CP]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < CP; ++c) w[c] = p2_make(wk[2 * c], wk[2 * c + 1]);
+            }
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                p2_fma(acc2[0][c][j], w[c], a0[j + kx]);
+                p2_fma(acc2[1][c][j], w[c], a1[j + kx]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a0[i] = a1[i];
+        }
+      } else {
+        float a0[8], a1[8];
+        {
+          const float4 lo = *reinterpret_cast<const float4*>(rowp);
+          const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
+          a0[0] = lo.x; a0[1] = lo.y; a0[2] = lo.z; a0[3] = lo.w;
+          a0[4] = hi.x; a0[5] = hi.y; a0[6] = hi.z; a0[7] = hi.w;
+        }
+#pragma unroll
+        for (int kz = 0; kz < K; ++kz) {
+          {
+            const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
+            const float4 lo = *reinterpret_cast<const float4*>(r1);
+            const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
+            a1[0] = lo.x; a1[1] = lo.y; a1[2] = lo.z; a1[3] = lo.w;
+            a1[4] = hi.x; a1[5] = hi.y; a1[6] = hi.z; a1[7] = hi.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float* wk = wp + (kz * K * K + kx) * C;
+            float w[COT];
+#pragma unroll
+            for (int c = 0; c < COT; ++c) w[c] = wk[c];
+#pragma unroll
+            for (int c = 0; c < COT; ++c) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[0][c][j] = fmaf(w[c], a0[j + kx], acc[0][c][j]);
+                acc[1][c][j] = fmaf(w[c], a1[j + kx], acc[1][c][j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a0[i] = a1[i];
+        }
+      }
+    }
+  }
+}
+
+
+// TMA = true: the input tile is fetched by the TMA unit (cp.async.bulk.tensor.5d, out-of-bounds = conv halo =
+// zero fill) and the weight chunk by a 1-D bulk copy, double buffered behind two mbarriers, so chunk ch+1
+// streams in while the CTA computes on chunk ch.  TMA = false: cooperative register-staged copy (tmap unused).
+template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA>
+__global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC>::THREADS, MINB)
+    k_conv_s1(const __grid_constant__ CUtensorMap tmap, ConvS1Params p) {
+  constexpr int XSH = TMA ? (4 - PAD % 4) % 4 : 0;
+  using G = ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC, XSH>;
   constexpr int COT = G::COT;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_in = smem;
   float* s_w = smem + G::IN_FLOATS;
   const int tid = threadIdx.x;
@@ -88,6 +198,38 @@ __global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC
       for (int j = 0; j < 4; ++j) acc[a][c][j] = 0.f;
   }
 
+  if constexpr (TMA) {
+    static_assert((G::W_FLOATS * 4) % 16 == 0, "bulk copy granularity");
+    constexpr int NCH = CI / CIC;
+    constexpr uint32_t BYTES = (uint32_t)(G::IN_FLOATS + G::W_FLOATS) * 4u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * G::STAGE);
+    if (tid == 0) {
+      tma::mbar_init(bar, 1);
+      tma::mbar_init(bar + 1, 1);
+      tma::fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int ch) {
+      float* dst = smem + (ch & 1) * G::STAGE;
+      tma::mbar_arrive_expect_tx(bar + (ch & 1), BYTES);
+      tma::load_5d(dst, &tmap, bar + (ch & 1), -(PAD + XSH), y0 - PAD, z0 - PAD, ch * CIC, b);
+      tma::load_1d(dst + G::IN_AL, p.Wp + (size_t)ch * G::W_FLOATS, (uint32_t)G::W_FLOATS * 4u, bar + (ch & 1));
+    };
+    if (tid == 0) {
+      issue(0);
+      if (NCH > 1) issue(1);
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+      tma::mbar_wait(bar + (ch & 1), (uint32_t)(ch >> 1) & 1u);
+      const float* st = smem + (ch & 1) * G::STAGE;
+      if (active) conv_s1_chunk<G, K, C, CIC, COT, CP, PAIR, XSH>(st, st + G::IN_AL, zp, ty, xg, cg, acc2, acc);
+      if (ch + 2 < NCH) {
+        __syncthreads();               // every thread is done reading this stage
+        if (tid == 0) issue(ch + 2);
+      }
+    }
+  } else {
   const float* in_b = p.in + (size_t)b * CI * DIN * DIN * G::IN_PITCH;
   constexpr int plane = DIN * G::IN_PITCH;
 
@@ -135,94 +277,8 @@ __global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC
       }
     }
     __syncthreads();
-    if (active) {
-#pragma unroll 1
-      for (int ci = 0; ci < CIC; ++ci) {
-#pragma unroll 1
-        for (int ky = 0; ky < K; ++ky) {
-          const float* rowp = s_in + ((ci * G::TZI + 2 * zp) * G::TYI + ty + ky) * G::PI + 4 * xg;
-          const float* wp = s_w + ((ci * K) * K + ky) * K * C + cg * COT;
-          if constexpr (PAIR) {
-            p2 a0[8], a1[8];
-            {
-              const float4 lo = *reinterpret_cast<const float4*>(rowp);
-              const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
-              a0[0] = p2_bcast(lo.x); a0[1] = p2_bcast(lo.y); a0[2] = p2_bcast(lo.z); a0[3] = p2_bcast(lo.w);
-              a0[4] = p2_bcast(hi.x); a0[5] = p2_bcast(hi.y); a0[6] = p2_bcast(hi.z); a0[7] = p2_bcast(hi.w);
-            }
-#pragma unroll
-            for (int kz = 0; kz < K; ++kz) {
-              {
-                const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
-                const float4 lo = *reinterpret_cast<const float4*>(r1);
-                const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
-                a1[0] = p2_bcast(lo.x); a1[1] = p2_bcast(lo.y); a1[2] = p2_bcast(lo.z); a1[3] = p2_bcast(lo.w);
-                a1[4] = p2_bcast(hi.x); a1[5] = p2_bcast(hi.y); a1[6] = p2_bcast(hi.z); a1[7] = p2_bcast(hi.w);
-              }
-#pragma unroll
-              for (int kx = 0; kx < K; ++kx) {
-                const float* wk = wp + (kz * K * K + kx) * C;
-                p2 w[CP];
-                if constexpr (COT == 8) {
-                  p2_ld2(wk, w[0], w[1]);
-                  p2_ld2(wk + 4, w[2 % CP], w[3 % CP]);
-                } else if constexpr (COT == 4) {
-                  p2_ld2(wk, w[0], w[1 % CP]);
-                } else {
-#pragma unroll
-                  for (int c = 0; c < CP; ++c) w[c] = p2_make(wk[2 * c], wk[2 * c + 1]);
-                }
-#pragma unroll
-                for (int c = 0; c < CP; ++c) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    p2_fma(acc2[0][c][j], w[c], a0[j + kx]);
-                    p2_fma(acc2[1][c][j], w[c], a1[j + kx]);
-                  }
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a0[i] = a1[i];
-            }
-          } else {
-            float a0[8], a1[8];
-            {
-              const float4 lo = *reinterpret_cast<const float4*>(rowp);
-              const float4 hi = *reinterpret_cast<const float4*>(rowp + 4);
-              a0[0] = lo.x; a0[1] = lo.y; a0[2] = lo.z; a0[3] = lo.w;
-              a0[4] = hi.x; a0[5] = hi.y; a0[6] = hi.z; a0[7] = hi.w;
-            }
-#pragma unroll
-            for (int kz = 0; kz < K; ++kz) {
-              {
-                const float* r1 = rowp + (kz + 1) * G::TYI * G::PI;
-                const float4 lo = *reinterpret_cast<const float4*>(r1);
-                const float4 hi = *reinterpret_cast<const float4*>(r1 + 4);
-                a1[0] = lo.x; a1[1] = lo.y; a1[2] = lo.z; a1[3] = lo.w;
-                a1[4] = hi.x; a1[5] = hi.y; a1[6] = hi.z; a1[7] = hi.w;
-              }
-#pragma unroll
-              for (int kx = 0; kx < K; ++kx) {
-                const float* wk = wp + (kz * K * K + kx) * C;
-                float w[COT];
-#pragma unroll
-                for (int c = 0; c < COT; ++c) w[c] = wk[c];
-#pragma unroll
-                for (int c = 0; c < COT; ++c) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    acc[0][c][j] = fmaf(w[c], a0[j + kx], acc[0][c][j]);
-                    acc[1][c][j] = fmaf(w[c], a1[j + kx], acc[1][c][j]);
-                  }
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a0[i] = a1[i];
-            }
-          }
-        }
-      }
-    }
+    if (active) conv_s1_chunk<G, K, C, CIC, COT, CP, PAIR, XSH>(s_in, s_w, zp, ty, xg, cg, acc2, acc);
+  }
   }
   if constexpr (PAIR) {
 #pragma unroll
@@ -316,7 +372,7 @@ struct WgradS1Cfg {
 template <int C, int DG, int TYG, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
   using G = WgradS1Cfg<C, DG, TYG>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_a = smem;
   float* s_g = smem + G::A_FLOATS;
   const int tid = threadIdx.x;

@@ -46,7 +46,7 @@ struct ConvTFwdCfg {
 template <int CI, int CO, int DIN, int MINB>
 __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_convT5_fwd(ConvTFwdParams p) {
   using G = ConvTFwdCfg<CI, CO, DIN>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_in = smem;
   float* s_w = smem + G::IN_FLOATS;
   const int tid = threadIdx.x;
@@ -207,7 +207,7 @@ struct ConvTDgradCfg {
 template <int CG, int CX, int DIN, int TY, int CGC, int MINB>
 __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, MINB) k_convT5_dgrad(ConvTDgradParams p) {
   using G = ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_g = smem;
   float* s_w = smem + G::G_FLOATS;
   const int tid = threadIdx.x;
@@ -369,7 +369,7 @@ struct ConvTWgradCfg {
 template <int CI, int CO, int DIN, int TYB, int CIB, int MINB>
 __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) {
   using G = ConvTWgradCfg<CI, CO, DIN, TYB, CIB>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_g = smem;
   float* s_x = smem + G::G_FLOATS;
   const int tid = threadIdx.x;

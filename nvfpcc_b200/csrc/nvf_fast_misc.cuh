@@ -42,7 +42,7 @@ struct ClsWgradCfg {
 template <int C, int D, int TYB, int ZSEG>
 __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
   using G = ClsWgradCfg<C, D, TYB, ZSEG>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* s_a = smem;
   float* s_g = smem + G::A_FLOATS;
   const int tid = threadIdx.x;
@@ -155,7 +155,7 @@ struct IgdnParamParams {
   int32_t n, C;
 };
 __global__ void __launch_bounds__(256) k_igdn_param(IgdnParamParams p) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int C = p.C;
   float* sx2 = smem;             // [C][64]  x^2
   float* st = smem + C * 64;     // [C][64]  t
