@@ -410,9 +410,9 @@ __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
       // the (g_c, g_c+1) operand pairs of two x positions
       for (int i = tid; i < C * TYG * NVG; i += 256) {
         const int c = i / (TYG * NVG), rem = i - c * (TYG * NVG);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(gb + (size_t)c * DG * DG * G::GP) + rem);
+        const float* sg = gb + (size_t)c * DG * DG * G::GP + 4 * rem;
         float* d = s_g + ((c >> 1) * TYG * G::GP + rem * 4) * 2 + (c & 1);
-        d[0] = v.x; d[2] = v.y; d[4] = v.z; d[6] = v.w;
+        tma::cp_async4(d, sg); tma::cp_async4(d + 2, sg + 1); tma::cp_async4(d + 4, sg + 2); tma::cp_async4(d + 6, sg + 3);
       }
       constexpr int NVA = G::APG / 4;
       constexpr int RA = TYG + 3;
@@ -423,9 +423,10 @@ __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
         const int ry = t % RA; t /= RA;
         const int sz = t & 3; t >>= 2;
         const int c = t;
-        *reinterpret_cast<float4*>(s_a + (c * 4 + sz) * G::ZSA + ry * G::AP + 4 * xv) =
-            __ldg(reinterpret_cast<const float4*>(ab + ((size_t)c * G::DA + sz) * G::DA * G::APG + (size_t)ry * G::APG) + xv);
+        tma::cp_async16(s_a + (c * 4 + sz) * G::ZSA + ry * G::AP + 4 * xv,
+                        ab + ((size_t)c * G::DA + sz) * G::DA * G::APG + (size_t)ry * G::APG + 4 * xv);
       }
+      tma::cp_async_wait_all();
     }
     __syncthreads();
     // ---- bias gradient side sum (all threads, C channels x DB_PARTS parts)

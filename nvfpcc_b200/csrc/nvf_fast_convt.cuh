@@ -65,10 +65,9 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
       const int t = q % 3; q /= 3;
       const int ci = q;
       const int iz = ((z - pz) >> 1) - t, iy = r - 2, ix = 4 * cv - 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < NT && iz >= 0 && iz < DIN && iy >= 0 && iy < DIN && ix >= 0 && ix < DIN)
-        v = __ldg(reinterpret_cast<const float4*>(in_b + (((size_t)ci * DIN + iz) * DIN + iy) * G::IN_PITCH + ix));
-      *reinterpret_cast<float4*>(s_in + ((ci * 3 + t) * G::TR + r) * G::IP + 4 * cv) = v;
+      const bool ok = t < NT && iz >= 0 && iz < DIN && iy >= 0 && iy < DIN && ix >= 0 && ix < DIN;
+      tma::cp_async16(s_in + ((ci * 3 + t) * G::TR + r) * G::IP + 4 * cv,
+                      ok ? in_b + (((size_t)ci * DIN + iz) * DIN + iy) * G::IN_PITCH + ix : in_b, ok);
     }
     constexpr int TAPV = 25 * CO / 4;
     for (int i = tid; i < CI * 3 * TAPV; i += G::THREADS) {
@@ -76,10 +75,9 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
       const int v4 = q % TAPV; q /= TAPV;
       const int t = q % 3; q /= 3;
       const int ci = q;
-      if (t < NT)
-        reinterpret_cast<float4*>(s_w)[i] =
-            __ldg(reinterpret_cast<const float4*>(p.Wp + ((size_t)(ci * 5 + pz + 2 * t) * 25) * CO) + v4);
+      if (t < NT) tma::cp_async16(s_w + 4 * i, p.Wp + ((size_t)(ci * 5 + pz + 2 * t) * 25) * CO + 4 * v4);
     }
+    tma::cp_async_wait_all();
   }
   __syncthreads();
   if (tid >= G::THREADS_USED) return;
@@ -244,11 +242,12 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
         const int rr = q % G::GR; q /= G::GR;
         const int s = q % 5; q /= 5;
         const int c = q;
-        *reinterpret_cast<float4*>(s_g + ((c * 5 + s) * G::GR + rr) * G::GPS + 4 * cv) = __ldg(
-            reinterpret_cast<const float4*>(g_b + (((size_t)(c0 + c) * G::DG + 2 * z + s) * G::DG + 2 * y0 + rr) * G::GP) + cv);
+        tma::cp_async16(s_g + ((c * 5 + s) * G::GR + rr) * G::GPS + 4 * cv,
+                        g_b + (((size_t)(c0 + c) * G::DG + 2 * z + s) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv);
       }
-      const float4* src = reinterpret_cast<const float4*>(p.Wp + (size_t)c0 * 125 * CX);
-      for (int i = tid; i < G::W_FLOATS / 4; i += G::THREADS) reinterpret_cast<float4*>(s_w)[i] = __ldg(src + i);
+      const float* src = p.Wp + (size_t)c0 * 125 * CX;
+      for (int i = tid; i < G::W_FLOATS / 4; i += G::THREADS) tma::cp_async16(s_w + 4 * i, src + 4 * i);
+      tma::cp_async_wait_all();
     }
     __syncthreads();
     if (active) {
@@ -402,8 +401,8 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
         const int rr = t % G::GR; t /= G::GR;
         const int s = t % 5; t /= 5;
         const int c = t;
-        *reinterpret_cast<float4*>(s_g + c * G::CSTR + s * G::SLICE + rr * G::ROWP + 4 * cv) = __ldg(
-            reinterpret_cast<const float4*>(gb + (((size_t)c * G::DG + 2 * z + s) * G::DG + 2 * y0 + rr) * G::GP) + cv);
+        tma::cp_async16(s_g + c * G::CSTR + s * G::SLICE + rr * G::ROWP + 4 * cv,
+                        gb + (((size_t)c * G::DG + 2 * z + s) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv);
       }
       constexpr int XV = DIN / 4;
       const float* xb = p.x + ((size_t)b * CI + cig * CIB) * DIN * DIN * DIN;
@@ -413,10 +412,11 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
         const int rr = t % TYB; t /= TYB;
         const int c = t;
         // s_x[c/2][rr][x][c&1]: channel pairs interleaved (one LDS.128 = the operand pairs of two x)
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (((size_t)c * DIN + z) * DIN + y0 + rr) * DIN) + cv);
+        const float* sx = xb + (((size_t)c * DIN + z) * DIN + y0 + rr) * DIN + 4 * cv;
         float* d = s_x + (((c >> 1) * TYB + rr) * DIN + 4 * cv) * 2 + (c & 1);
-        d[0] = v.x; d[2] = v.y; d[4] = v.z; d[6] = v.w;
+        tma::cp_async4(d, sx); tma::cp_async4(d + 2, sx + 1); tma::cp_async4(d + 4, sx + 2); tma::cp_async4(d + 6, sx + 3);
       }
+      tma::cp_async_wait_all();
     }
     __syncthreads();
     if (active) {

@@ -92,6 +92,17 @@ __device__ __forceinline__ void load_1d(void* dst, const void* src, uint32_t byt
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// ---- Ampere-style asynchronous copies (LDGSTS): all loads of a staging loop are in flight at once, no
+// register round trip.  src_bytes = 0 zero-fills the destination (convolution halo); src must still be a
+// valid address.
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid = true) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
 }  // namespace tma
