@@ -221,7 +221,7 @@ struct DevLauncher {
   int sms() const { return n_sms; }
   int error() const { return rc; }
 
-  void pack(const PackParams& p) { k_pack<<<32, kThreads, 0, st>>>(p); post(); }
+  void pack(const PackParams& p) { k_pack<<<n_sms > 0 ? n_sms : 32, kThreads, 0, st>>>(p); post(); }
   void fusedA(const FusedAParams& p, int grid) {
     static bool attr_set = false;
     if (!attr_set) {

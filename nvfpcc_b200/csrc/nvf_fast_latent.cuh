@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(kLatentThreads) k_latent_fwd(LatentKParams p) 
 template <int CH>
 __global__ void __launch_bounds__(kLatentThreads) k_latent_bwd(LatentKParams p) {
   constexpr int NP = LatentCfg<CH>::NP_BWD;
-  __shared__ double sm[kLatentThreads / 32];
   float W[CH][CH], bias[CH], beta[CH], gamma[CH][CH];
   latent_load_params<CH>(p, W, bias, beta, gamma);
   const bool want_params = p.gk != nullptr;
@@ -226,10 +225,21 @@ __global__ void __launch_bounds__(kLatentThreads) k_latent_bwd(LatentKParams p) 
     }
   }
   if (!want_params) return;
+  {
+    // fixed-order CTA sums of the NP partial gradients: warp shuffles, then one pass over the warps
+    __shared__ double smp[NP][kLatentThreads / 32];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    const double s = cta_sum_d((double)acc[i], sm);
-    if (threadIdx.x == 0) p.partial[(size_t)blockIdx.x * NP + i] = s;
+    for (int i = 0; i < NP; ++i) {
+      double v = (double)acc[i];
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) smp[i][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP) {
+      double s = 0.0;
+      for (int w = 0; w < kLatentThreads / 32; ++w) s += smp[threadIdx.x][w];
+      p.partial[(size_t)blockIdx.x * NP + threadIdx.x] = s;
+    }
   }
   if (!last_cta(p.ticket)) return;
   for (int i = threadIdx.x; i < NP; i += kLatentThreads) {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "nvf_common.h"
+#include "nvf_tma.cuh"
 
 namespace nvf {
 namespace fast {
@@ -18,8 +19,9 @@ struct ClsWgradParams {
   int32_t n;
 };
 
-// One CTA = (block, row band, z segment): it streams along z with a ring of three staged
-// input slices (each slice is fetched once per CTA instead of three times).
+// One CTA = (block, row band, z segment): it streams along z with a ring of four staged input
+// slices (each slice is fetched once per CTA instead of three times); slice z+2 and the g rows of
+// z+1 stream in with cp.async while slice z is being consumed.
 template <int C, int D, int TYB, int ZSEG>
 struct ClsWgradCfg {
   static constexpr int SETT = C * 9;
@@ -27,12 +29,12 @@ struct ClsWgradCfg {
   static constexpr int PI = D + 4;                 // tile col c <-> ix = c - 1
   static constexpr int RA = TYB + 2;
   static constexpr int SLOT = C * RA * PI;         // one staged slice
-  static constexpr int A_FLOATS = 3 * SLOT;
-  static constexpr int G_FLOATS = TYB * D;
+  static constexpr int A_FLOATS = 4 * SLOT;
+  static constexpr int G_FLOATS = TYB * D;        // one of two g buffers
   static constexpr int NW = C * 27;
   static constexpr int OUT_FLOATS = NW + 1;
   static constexpr int RED_FLOATS = NSET * NW + 256;
-  static constexpr int SMEM_FLOATS = (A_FLOATS + G_FLOATS) > RED_FLOATS ? (A_FLOATS + G_FLOATS) : RED_FLOATS;
+  static constexpr int SMEM_FLOATS = (A_FLOATS + 2 * G_FLOATS) > RED_FLOATS ? (A_FLOATS + 2 * G_FLOATS) : RED_FLOATS;
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
   static constexpr int BANDS = D / TYB;
   static constexpr int SEGS = D / ZSEG;
@@ -62,9 +64,9 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
   const int y0 = band * TYB, z0 = seg * ZSEG;
   const float* ab = p.a + (size_t)b * C * D * D * D;
 
-  // stage input slice iz into ring slot (iz + 3) % 3 (zero outside the block: padding 1)
+  // stage input slice iz into ring slot (iz + 4) % 4 (zero outside the block: padding 1), asynchronously
   auto stage = [&](int iz) {
-    float* dst = s_a + ((iz + 3) % 3) * G::SLOT;
+    float* dst = s_a + ((iz + 4) & 3) * G::SLOT;
     constexpr int NV = D / 4;
     for (int i = tid; i < C * G::RA * NV; i += 256) {
       int t = i;
@@ -72,35 +74,42 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
       const int rr = t % G::RA; t /= G::RA;
       const int ch = t;
       const int iy = y0 + rr - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iz >= 0 && iz < D && iy >= 0 && iy < D)
-        v = __ldg(reinterpret_cast<const float4*>(ab + (((size_t)ch * D + iz) * D + iy) * D) + xv);
+      const bool ok = iz >= 0 && iz < D && iy >= 0 && iy < D;
+      const float* src = ok ? ab + (((size_t)ch * D + iz) * D + iy) * D + 4 * xv : ab;
       float* d = dst + (ch * G::RA + rr) * G::PI + 1 + 4 * xv;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      tma::cp_async4z(d, src, ok); tma::cp_async4z(d + 1, src + 1, ok);
+      tma::cp_async4z(d + 2, src + 2, ok); tma::cp_async4z(d + 3, src + 3, ok);
     }
   };
+  auto stage_g = [&](int z) {
+    const float* gb = p.g + (((size_t)b * D + z) * D + y0) * D;
+    float* dst = s_g + (z & 1) * G::G_FLOATS;
+    for (int i = tid; i < G::G_FLOATS / 4; i += 256) tma::cp_async16(dst + 4 * i, gb + 4 * i);
+  };
   // the two halo columns of every staged row stay zero for the whole kernel
-  for (int i = tid; i < 3 * C * G::RA; i += 256) {
+  for (int i = tid; i < 4 * C * G::RA; i += 256) {
     s_a[i * G::PI] = 0.f;
     s_a[i * G::PI + D + 1] = 0.f;
   }
   stage(z0 - 1);
   stage(z0);
+  stage(z0 + 1);
+  stage_g(z0);
   for (int z = z0; z < z0 + ZSEG; ++z) {
-    stage(z + 1);
-    {
-      const float* gb = p.g + (((size_t)b * D + z) * D + y0) * D;
-      for (int i = tid; i < G::G_FLOATS / 4; i += 256)
-        reinterpret_cast<float4*>(s_g)[i] = __ldg(reinterpret_cast<const float4*>(gb) + i);
+    tma::cp_async_wait_all();
+    __syncthreads();                 // slices z-1..z+1 and g(z) have landed; everyone is done with z-1
+    if (z + 1 < z0 + ZSEG) {
+      stage(z + 2);                  // overwrites the slot of slice z-2
+      stage_g(z + 1);
     }
-    __syncthreads();
+    const float* sg = s_g + (z & 1) * G::G_FLOATS;
     {
       float s = 0.f;
-      for (int i = tid; i < G::G_FLOATS; i += 256) s += s_g[i];
+      for (int i = tid; i < G::G_FLOATS; i += 256) s += sg[i];
       dbacc += s;
     }
     if (active) {
-      const float* a_base = s_a + ((z + kz - 1 + 3) % 3) * G::SLOT + (ci * G::RA + ky) * G::PI;
+      const float* a_base = s_a + ((z + kz - 1 + 4) & 3) * G::SLOT + (ci * G::RA + ky) * G::PI;
       for (int rr = set; rr < TYB; rr += G::NSET) {
 #pragma unroll
         for (int xo = 0; xo < D / 8; ++xo) {
@@ -109,8 +118,8 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
           const float4 a1 = *reinterpret_cast<const float4*>(ar + 4);
           const float2 a2 = *reinterpret_cast<const float2*>(ar + 8);
           const float av[10] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
-          const float4 g0 = *reinterpret_cast<const float4*>(s_g + rr * D + 8 * xo);
-          const float4 g1 = *reinterpret_cast<const float4*>(s_g + rr * D + 8 * xo + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(sg + rr * D + 8 * xo);
+          const float4 g1 = *reinterpret_cast<const float4*>(sg + rr * D + 8 * xo + 4);
           const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -119,8 +128,8 @@ __global__ void __launch_bounds__(256) k_cls_wgrad(ClsWgradParams p) {
         }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   float* red = smem;
   if (active) {
 #pragma unroll
