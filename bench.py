@@ -233,22 +233,36 @@ class TrainWorkload:
 
     def step(self, i, host_inputs):
         """One weight-loop step (NVFPCC.py:149-223): batch -> static buffers -> fused fwd + loss + bwd +
-        all-reduce + Adam (one CUDA-graph replay).  host_inputs: the batch's gt/dist come from pinned HOST
-        memory and the loss is read back (the reference's DataLoader + .item() path)."""
-        if host_inputs:
-            idx = self.batch_idx(i)
-            gt = self.gt_host[idx].pin_memory()
-            dst = self.dist_host[idx].pin_memory()
-            st = self.ws.step(self.emb[idx.cuda()], gt, dst, q=1)
-            self.last_loss = st[0].item()                        # D2H of the step's result
-        else:
-            idx = self.idx_dev[i % len(self.idx_dev)]
-            st = self.ws.step(self.emb[idx], self.gt_dev[idx], self.dist_dev[idx], q=1)
-            self.last_loss = st[0]
+        all-reduce + Adam (one CUDA-graph replay), inputs resident in HBM."""
+        idx = self.idx_dev[i % len(self.idx_dev)]
+        st = self.ws.step(self.emb[idx], self.gt_dev[idx], self.dist_dev[idx], q=1)
+        self.last_loss = st[0]
         return st
 
+    def e2e_loop(self, first, steps):
+        """`steps` weight-loop steps fed from HOST memory through the public API (trainer.HostBatchFeeder +
+        trainer.WeightStep): every step's gt/dist batch is gathered from the host dataset into pinned memory,
+        copied H2D, and every step's loss is read back D2H - the reference's DataLoader / .to(device) / .item()
+        path (NVFPCC.py:149-223) - with the copies of step i+1 overlapping the kernels of step i."""
+        from nvfpcc_b200 import trainer
+        if not hasattr(self, "feeder"):
+            self.feeder = trainer.HostBatchFeeder(self.gt_host, self.dist_host, self.B)
+            self.emb_batches = [self.emb[self.batch_idx(i).cuda()] for i in range(max(1, self.nb // self.B))]
+        f = self.feeder
+        f.submit(self.batch_idx(first))
+        for i in range(first, first + steps):
+            (gt, dst), slot = f.take()
+            st = self.ws.step(self.emb_batches[i % len(self.emb_batches)], gt, dst, q=1)
+            f.release(slot)
+            if i + 1 < first + steps:
+                f.submit(self.batch_idx(i + 1))        # overlaps the kernels of step i
+            prev = f.read_stats(st)                     # D2H of this step's result; returns the previous step's
+            if prev is not None:
+                self.last_loss = float(prev[0])
+        self.last_loss = float(f.drain()[0])
+
     h2d_bytes = 2 * 16 * 32768 * 4
-    d2h_bytes = 4
+    d2h_bytes = 7 * 4
 
 
 class DecodeWorkload:
@@ -292,7 +306,7 @@ def oracle_state(chanstr):
     return O.make_state(3, [int(c) for c in chanstr.split(",")], synth.synthetic_seed())
 
 
-def cpu_train_baseline(args, pts, origins, budget_s=20.0, max_steps=None):
+def cpu_train_baseline(args, pts, origins, budget_s=20.0, max_steps=None, warmup=1):
     """The reference algorithm (oracle port, torch CPU fp32, all host threads) on the same train
     workload: one weight-loop step = forward + losses + backward + Adam at batch 16."""
     from nvfpcc_b200 import synth
@@ -314,7 +328,8 @@ def cpu_train_baseline(args, pts, origins, budget_s=20.0, max_steps=None):
         L["loss"].backward()
         opt.step()
 
-    one()
+    for _ in range(max(1, warmup)):
+        one()
     t0 = time.perf_counter()
     n = 0
     while True:
@@ -354,7 +369,7 @@ def run_reference(args):
     if rank != 0:
         return
     pts, origins = make_cloud(args.resolution)
-    cb, sec_per = cpu_train_baseline(args, pts, origins, max_steps=(args.steps + args.warmup))
+    cb, sec_per = cpu_train_baseline(args, pts, origins, max_steps=args.steps, warmup=args.warmup)
     dec = cpu_decode_baseline(args, origins)
     line = dict(impl="reference", metric="train_blocks_per_sec", value=cb["value"], unit="blocks/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec_per * 1e3,
@@ -402,12 +417,10 @@ def main():
     launches = (binding.launch_count() - launches0) if args.no_graph else tw.ws.launches_per_step * args.steps
     ms_step = ms_total / args.steps
     train_value = HP["batch"] * world / (ms_step * 1e-3)
-    for i in range(2):
-        tw.step(i, True)
+    tw.e2e_loop(0, 3)
     barrier_sync(world)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        tw.step(args.warmup + i, True)
+    tw.e2e_loop(args.warmup, args.steps)
     barrier_sync(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
     train_e2e = HP["batch"] * world / (e2e_ms * 1e-3)

@@ -203,6 +203,81 @@ class WeightStep:
         return self.stats
 
 
+class HostBatchFeeder:
+    """Host -> device input pipeline for the weight loop (the reference's DataLoader + `.to(device)`,
+    NVFPCC.py:109-111,152-153, and its per-step `.item()` read, :190-221), double buffered:
+
+    * `submit(idx)` gathers the batch's gt / dist rows from the host dataset into one of two PINNED staging
+      buffers and enqueues their H2D copies on a dedicated copy stream (no allocation, no host sync);
+    * `take()` makes the compute stream wait for the oldest submitted batch and returns its device tensors;
+    * `read_stats(stats)` enqueues an asynchronous D2H copy of a step's stats into pinned memory and returns the
+      stats of the PREVIOUS step (already landed), so the host reads every step's result without draining the GPU.
+
+    With this, the copies and the CPU-side gather of step i+1 overlap the kernels of step i."""
+
+    def __init__(self, gt_host: torch.Tensor, dist_host: torch.Tensor, batch: int, device=None):
+        dev = torch.device(device if device is not None else "cuda")
+        self.gt_host, self.dist_host = gt_host, dist_host
+        shape = (batch,) + tuple(gt_host.shape[1:])
+        self.pin = [(torch.empty(shape, dtype=gt_host.dtype).pin_memory(), torch.empty(shape, dtype=dist_host.dtype).pin_memory())
+                    for _ in range(2)]
+        self.dev = [(torch.empty(shape, dtype=torch.float32, device=dev), torch.empty(shape, dtype=torch.float32, device=dev))
+                    for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self._head = self._tail = 0
+        self.stats_pin = [torch.zeros(len(STAT_NAMES)).pin_memory() for _ in range(2)]
+        self.stats_ev = [None, None]
+        self._stat_i = 0
+        self.bytes_per_batch = sum(t.numel() * t.element_size() for t in self.pin[0])
+
+    def submit(self, idx: torch.Tensor) -> None:
+        s = self._head & 1
+        if self._head >= 2:
+            self.h2d_done[s].synchronize()           # the pinned buffer's previous H2D has finished
+        torch.index_select(self.gt_host, 0, idx, out=self.pin[s][0])
+        torch.index_select(self.dist_host, 0, idx, out=self.pin[s][1])
+        with torch.cuda.stream(self.copy_stream):
+            if self._head >= 2:
+                self.copy_stream.wait_event(self.consumed[s])   # the device buffer's previous consumer is done
+            self.dev[s][0].copy_(self.pin[s][0], non_blocking=True)
+            self.dev[s][1].copy_(self.pin[s][1], non_blocking=True)
+            self.h2d_done[s].record(self.copy_stream)
+            self.ready[s].record(self.copy_stream)
+        self._head += 1
+
+    def take(self):
+        s = self._tail & 1
+        torch.cuda.current_stream().wait_event(self.ready[s])
+        self._tail += 1
+        return self.dev[s], s
+
+    def release(self, slot: int) -> None:
+        """Call after the consumer of `slot` has been enqueued on the compute stream."""
+        self.consumed[slot].record(torch.cuda.current_stream())
+
+    def read_stats(self, stats: torch.Tensor) -> Optional[torch.Tensor]:
+        i = self._stat_i & 1
+        self.stats_pin[i].copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stats_ev[i] = ev
+        self._stat_i += 1
+        prev = self.stats_ev[i ^ 1]
+        if prev is None:
+            return None
+        prev.synchronize()
+        return self.stats_pin[i ^ 1]
+
+    def drain(self) -> torch.Tensor:
+        """Stats of the most recent step (blocks until it has finished)."""
+        i = (self._stat_i - 1) & 1
+        self.stats_ev[i].synchronize()
+        return self.stats_pin[i]
+
+
 class EmbeddingStep:
     """The once-per-epoch update of all embeddings (NVFPCC.py:225-251): one full-batch forward +
     backward w.r.t. the embeddings only (the weight gradients of this pass are discarded by the
