@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--decode-steps", type=int, default=5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly (no CUDA graph)")
+    ap.add_argument("--skip-epoch", action="store_true", help="skip the embedding-loop / epoch measurement")
     return ap.parse_args()
 
 
@@ -299,6 +300,30 @@ class DecodeWorkload:
         return r
 
 
+def embedding_loop(tw, args, world, n_blocks, flush):
+    """The once-per-epoch embedding update (NVFPCC.py:225-251): ONE full-batch forward + backward over all of the
+    rank's leaf blocks w.r.t. the embeddings (weight gradients skipped: the reference discards them) + Adam on
+    the embeddings.  gt/dist of the `train_blocks` distinct synthetic blocks are tiled to `n_blocks`."""
+    from nvfpcc_b200 import _lib, trainer
+    bind = _lib.cuda_binding()
+    per_block = bind.workspace_bytes(bind.desc(3, [int(c) for c in args.chanstr.split(",")]), 64, _lib.NVF_MODE_TRAIN) / 64
+    n_full, scale = n_blocks, 1.0
+    if n_blocks * per_block > 40e9:            # bound the activation stash: measure a slice, scale linearly
+        n_blocks = int(40e9 / per_block)
+        scale = n_full / n_blocks
+    reps = (n_blocks + tw.nb - 1) // tw.nb
+    gt = tw.gt_dev.repeat(reps, 1, 1, 1, 1)[:n_blocks].contiguous()
+    dst = tw.dist_dev.repeat(reps, 1, 1, 1, 1)[:n_blocks].contiguous()
+    emb = torch.ones(n_blocks, 3, 2, 2, 2, device="cuda", requires_grad=True)
+    opt_emb = torch.optim.Adam([emb], lr=HP["lr"] * 5.0)                       # lr * wemb (NVFPCC.py:124)
+    es = trainer.EmbeddingStep(tw.net, emb, opt_emb, tw.n_total, HP["lmbda"], HP["w1"], HP["w2"])
+    es.step(gt, dst, 1)
+    ms = timed(lambda i: es.step(gt, dst, 1), 2, world, pre=lambda: flush_l2(flush)) / 2 * scale
+    del es, opt_emb, emb, gt, dst
+    torch.cuda.empty_cache()
+    return ms
+
+
 # ----------------------------------------------------------------------------- reference arm
 def oracle_state(chanstr):
     from nvfpcc_b200 import synth
@@ -425,6 +450,24 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
     train_e2e = HP["batch"] * world / (e2e_ms * 1e-3)
 
+    # ---------------- embedding loop / whole epoch ----------------
+    epoch = None
+    if not args.skip_epoch:
+        from nvfpcc_b200 import dist as D
+        lo, hi = D.block_range(origins.shape[0], rank, world)
+        emb_ms = embedding_loop(tw, args, world, hi - lo, flush)
+        n_all = origins.shape[0]
+        steps_a = (n_all + HP["batch"] * world - 1) // (HP["batch"] * world)     # weight-loop steps per epoch
+        epoch_ms = steps_a * ms_step + emb_ms
+        f_emb = F_TRAIN[args.chanstr] * 2.0 / 3.0                                # forward + data gradients
+        epoch = dict(blocks=int(n_all), weight_loop_steps=int(steps_a), weight_loop_ms=steps_a * ms_step,
+                     embedding_loop_ms=emb_ms, epoch_ms=epoch_ms, epochs_per_sec=1e3 / epoch_ms,
+                     block_passes_per_sec=2.0 * n_all / (epoch_ms * 1e-3),
+                     embedding_loop_tflops=(hi - lo) * f_emb / (emb_ms * 1e-3) / 1e12,
+                     note="one epoch of train() (NVFPCC.py:128-254) = weight loop over all blocks at batch 16 per GPU "
+                          "(measured per step above, x steps) + one full-batch embedding update (measured); "
+                          "embedding_loop_tflops counts forward + data-gradient FLOPs only (2/3 of F_train)")
+
     # ---------------- decode (second half of the metric) ----------------
     dw = DecodeWorkload(args, rank, world, pts, origins)
     for i in range(3):
@@ -483,6 +526,9 @@ def main():
                                   timing="CUDA events around the nvf_decode launch sequence (pack + fused kernel + scan + emit)",
                                   kernel="k_decode_fused_A" if cs == "8,16,8,8" else "layer-wise kernels")),
     )
+    if epoch is not None:
+        epoch["embedding_loop_frac_of_peak"] = epoch["embedding_loop_tflops"] / peak
+        line["epoch"] = epoch
     if not args.skip_cpu_baseline and world == 1:
         line["cpu_baseline"], _ = cpu_train_baseline(args, pts, origins, budget_s=15.0)
         line["decode"]["cpu_baseline"] = cpu_decode_baseline(args, origins, budget_s=10.0)
