@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "nvf_api_impl.h"
@@ -32,6 +33,36 @@ struct SidePool {
 SidePool g_side[kMaxDevices];
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
 
+
+// Optional programmatic stream serialisation (PDL), NVF_PDL=1: a kernel's CTAs may be scheduled while the
+// previous kernel of the stream is still draining; they block in griddepcontrol.wait (pdl_entry(), first
+// statement of every kernel) until that kernel has completed and flushed, so semantics are those of an
+// ordinary in-order stream.  Measured on B200 (round 1, graph-captured 16-block train step): 0.98 ms with PDL
+// vs 0.90 ms without - the early-resident waiting CTAs take the slots the side-stream weight-gradient kernels
+// would otherwise fill - so the default is OFF (plain launches; pdl_entry() is then a no-op).
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVF_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+template <class... KArgs, class... Args>
+void nvf_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k, KArgs(args)...);   // errors are picked up by the caller's cudaGetLastError()
+}
+
 template <class TS>
 struct DevEnv {
   TS ts;
@@ -44,22 +75,26 @@ struct DevEnv {
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(kThreads) k_pack(PackParams p) {
+  pdl_entry();
   pack_thread(p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_decode_fused_A(FusedAParams p) {
+  pdl_entry();
   extern __shared__ __align__(128) float smem[];
   DevEnv<FusedATS> env;
   FusedABlock<DevEnv<FusedATS>>::run(env, p, smem, blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(kThreads) k_scan_counts(EmitParams p) {
+  pdl_entry();
   __shared__ int64_t sm[2 * kThreads];
   DevEnv<int> env;
   ScanBlock<DevEnv<int>>::run(env, p, sm);
 }
 
 __global__ void __launch_bounds__(kThreads) k_emit_coords(EmitParams p) {
+  pdl_entry();
   __shared__ int sm[2 * kThreads];
   DevEnv<int> env;
   EmitBlock<DevEnv<int>>::run(env, p, sm, blockIdx.x);
@@ -67,29 +102,34 @@ __global__ void __launch_bounds__(kThreads) k_emit_coords(EmitParams p) {
 
 template <class K>
 __global__ void __launch_bounds__(kThreads) k_generic(typename K::Params p) {
+  pdl_entry();
   K::thread(p, blockIdx.x, threadIdx.x, gridDim.x);
 }
 
 template <int COT, int K>
 __global__ void __launch_bounds__(kThreads) k_wgrad(WgradParams p) {
+  pdl_entry();
   extern __shared__ __align__(128) float smem[];
   DevEnv<int> env;
   WgradBlock<COT, K>::run(env, p, smem, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kThreads) k_chansum(ChanSumParams p) {
+  pdl_entry();
   __shared__ float sm[kThreads];
   DevEnv<int> env;
   ChanSumBlock::run(env, p, sm, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kThreads) k_mask(MaskParams p) {
+  pdl_entry();
   __shared__ int sm[kThreads];
   DevEnv<int> env;
   MaskBlock::run(env, p, sm, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kThreads) k_loss(LossParams p) {
+  pdl_entry();
   __shared__ double sm[kThreads * NVF_LOSS_SUMS];
   DevEnv<int> env;
   LossBlock::run(env, p, sm, blockIdx.x);
@@ -98,6 +138,7 @@ __global__ void __launch_bounds__(kThreads) k_loss(LossParams p) {
 // FFMA throughput probes.  variant 0: scalar FFMA, 8x8 register tile (the shape
 // of the conv inner loops); variant 1: packed fma.rn.f32x2 on the same tile.
 __global__ void __launch_bounds__(kThreads) k_ffma(int variant, long long iters, float* sink) {
+  pdl_entry();
   float w[8], a[8];
   for (int i = 0; i < 8; ++i) {
     w[i] = 1.0f + 1e-6f * (threadIdx.x + i);
@@ -221,7 +262,7 @@ struct DevLauncher {
   int sms() const { return n_sms; }
   int error() const { return rc; }
 
-  void pack(const PackParams& p) { k_pack<<<n_sms > 0 ? n_sms : 32, kThreads, 0, st>>>(p); post(); }
+  void pack(const PackParams& p) { nvf_launch(k_pack, dim3(n_sms > 0 ? n_sms : 32), dim3(kThreads), (size_t)(0), st, p); post(); }
   void fusedA(const FusedAParams& p, int grid) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -229,11 +270,11 @@ struct DevLauncher {
         return;
       attr_set = true;
     }
-    k_decode_fused_A<<<grid, kThreads, FusedA::SMEM_BYTES, st>>>(p);
+    nvf_launch(k_decode_fused_A, dim3(grid), dim3(kThreads), (size_t)(FusedA::SMEM_BYTES), st, p);
     post();
   }
-  void scan(const EmitParams& p) { k_scan_counts<<<1, kThreads, 0, st>>>(p); post(); }
-  void emit(const EmitParams& p, int grid) { k_emit_coords<<<grid, kThreads, 0, st>>>(p); post(); }
+  void scan(const EmitParams& p) { nvf_launch(k_scan_counts, dim3(1), dim3(kThreads), (size_t)(0), st, p); post(); }
+  void emit(const EmitParams& p, int grid) { nvf_launch(k_emit_coords, dim3(grid), dim3(kThreads), (size_t)(0), st, p); post(); }
   template <int COT>
   void layer(const LayerParams& p) {
     const int64_t XT = (p.Dout + 3) >> 2;
@@ -242,23 +283,23 @@ struct DevLauncher {
     const int64_t cap = (int64_t)n_sms * 32;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k_generic<LayerKernel<COT>><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    nvf_launch(k_generic<LayerKernel<COT>>, dim3((unsigned)grid), dim3(kThreads), (size_t)(0), st, p);
     post();
   }
   template <int COT, int K>
   void wgrad(const WgradParams& p, int grid) {
     const int smem = kThreads * COT * K * (int)sizeof(float);
-    k_wgrad<COT, K><<<grid, kThreads, smem, st>>>(p);
+    nvf_launch(k_wgrad<COT, K>, dim3(grid), dim3(kThreads), (size_t)(smem), st, p);
     post();
   }
-  void chansum(const ChanSumParams& p, int grid) { k_chansum<<<grid, kThreads, 0, st>>>(p); post(); }
+  void chansum(const ChanSumParams& p, int grid) { nvf_launch(k_chansum, dim3(grid), dim3(kThreads), (size_t)(0), st, p); post(); }
   template <class K>
   void generic(const typename K::Params& p, int grid) {
-    k_generic<K><<<grid < 1 ? 1 : grid, kThreads, 0, st>>>(p);
+    nvf_launch(k_generic<K>, dim3(grid < 1 ? 1 : grid), dim3(kThreads), (size_t)(0), st, p);
     post();
   }
-  void mask(const MaskParams& p, int grid) { k_mask<<<grid, kThreads, 0, st>>>(p); post(); }
-  void loss(const LossParams& p, int grid) { k_loss<<<grid, kThreads, 0, st>>>(p); post(); }
+  void mask(const MaskParams& p, int grid) { nvf_launch(k_mask, dim3(grid), dim3(kThreads), (size_t)(0), st, p); post(); }
+  void loss(const LossParams& p, int grid) { nvf_launch(k_loss, dim3(grid), dim3(kThreads), (size_t)(0), st, p); post(); }
 
   // ---- shared-memory tiled kernels of the training path (nvf_fast_*.cuh) --------------------
   float* part_base = nullptr;   // scratch for split-K partial results (bump allocated per call)
@@ -283,7 +324,7 @@ struct DevLauncher {
     for (int i = 0; i < red.njobs; ++i) nmax = red.job[i].n_w + red.job[i].n_b > nmax ? red.job[i].n_w + red.job[i].n_b : nmax;
     int gx = (nmax + 31) / 32;
     if (gx > 1024) gx = 1024;
-    fast::k_reduce_partials<<<dim3(gx, red.njobs), 256, 0, st>>>(red);
+    nvf_launch(fast::k_reduce_partials, dim3(dim3(gx, red.njobs)), dim3(256), (size_t)(0), st, red);
     post();
     red.njobs = 0;
   }
@@ -308,7 +349,7 @@ struct DevLauncher {
       return true;
     }
     fast::ConvS1Params q{p.in, p.out, p.out2, p.Wp, p.bias, p.mask, p.n, p.act};
-    k<<<p.n * G::TILES_Z * G::TILES_Y, G::THREADS, SMEM, st>>>(map, q);
+    nvf_launch(k, dim3(p.n * G::TILES_Z * G::TILES_Y), dim3(G::THREADS), (size_t)(SMEM), st, map, q);
     post();
     return true;
   }
@@ -319,7 +360,7 @@ struct DevLauncher {
     auto* k = fast::k_convT5_fwd<CI, CO, DIN, MINB>;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::ConvTFwdParams q{p.in, p.out, p.Wp, p.bias, p.n};
-    k<<<p.n * G::DOUT, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    nvf_launch(k, dim3(p.n * G::DOUT), dim3(G::THREADS), (size_t)(G::SMEM_BYTES), st, q);
     post();
     return true;
   }
@@ -330,7 +371,7 @@ struct DevLauncher {
     auto* k = fast::k_convT5_dgrad<CG, CX, DIN, TY, CGC, MINB>;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::ConvTDgradParams q{p.in, p.out, p.Wp, p.add, p.mask, p.n};
-    k<<<p.n * DIN * G::BANDS, G::THREADS, G::SMEM_BYTES, st>>>(q);
+    nvf_launch(k, dim3(p.n * DIN * G::BANDS), dim3(G::THREADS), (size_t)(G::SMEM_BYTES), st, q);
     post();
     return true;
   }
@@ -398,7 +439,7 @@ struct DevLauncher {
     if (!partial) return false;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::WgradS1Params q{p.A, p.Sft, partial, p.n};
-    k<<<grid, 256, G::SMEM_BYTES, st>>>(q);
+    nvf_launch(k, dim3(grid), dim3(256), (size_t)(G::SMEM_BYTES), st, q);
     post();
     add_reduce(fast::ReduceJob{partial, p.dW, db, grid, G::OUT_FLOATS, G::NW, C, 0, 0});
     return true;
@@ -409,7 +450,7 @@ struct DevLauncher {
     float* partial = take_partial((size_t)c.n * zch * c.C);
     if (!partial) return false;
     fast::ChanSumFastParams q{c.g, partial, c.n, c.C, c.D, c.pitch, zch};
-    fast::k_chansum_fast<<<c.n * zch * c.C, 256, 0, st>>>(q);
+    nvf_launch(fast::k_chansum_fast, dim3(c.n * zch * c.C), dim3(256), (size_t)(0), st, q);
     post();
     add_reduce(fast::ReduceJob{partial, c.out, nullptr, c.n * zch, c.C, c.C, 0, 0, 0});
     return true;
@@ -428,7 +469,7 @@ struct DevLauncher {
     if (!chansum_fast(c)) return false;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::ConvTWgradParams q{p.A, p.Sft, partial, p.n};
-    k<<<dim3(grid, G::GROUPS), 224, G::SMEM_BYTES, st>>>(q);
+    nvf_launch(k, dim3(dim3(grid, G::GROUPS)), dim3(224), (size_t)(G::SMEM_BYTES), st, q);
     post();
     for (int grp = 0; grp < G::GROUPS; ++grp) {
       const int cog = grp % (CO / 8), cig = grp / (CO / 8);
@@ -448,7 +489,7 @@ struct DevLauncher {
     if (!partial) return false;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::ClsWgradParams q{p.A, p.Sft, partial, p.n};
-    k<<<grid, 256, G::SMEM_BYTES, st>>>(q);
+    nvf_launch(k, dim3(grid), dim3(256), (size_t)(G::SMEM_BYTES), st, q);
     post();
     add_reduce(fast::ReduceJob{partial, p.dW, db, grid, G::OUT_FLOATS, G::NW, 1, 0, 0});
     return true;
@@ -491,7 +532,7 @@ struct DevLauncher {
     if (!smem_attr(fast::k_stem_fwd, smem)) return true;
     fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
                           nullptr, nullptr, x0, a0, a1, nullptr, nullptr, n, d.ch, d.c0, d.c1};
-    fast::k_stem_fwd<<<n * 8, 256, smem, st>>>(q);
+    nvf_launch(fast::k_stem_fwd, dim3(n * 8), dim3(256), (size_t)(smem), st, q);
     post();
     if (cls0) {   // conv0_cls + sigmoid: auxiliary head, off the critical path
       LayerParams p{a1, cls0, cls0_wp, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
@@ -499,7 +540,7 @@ struct DevLauncher {
       side_begin();
       const bool ok = fast_layer(p);
       side_end();
-      if (!ok) k_generic<LayerKernel<1>><<<(n * 128 + kThreads - 1) / kThreads, kThreads, 0, st>>>(p), post();
+      if (!ok) { nvf_launch(k_generic<LayerKernel<1>>, dim3((n * 128 + kThreads - 1) / kThreads), dim3(kThreads), (size_t)(0), st, p); post(); }
     }
     return true;
   }
@@ -518,9 +559,9 @@ struct DevLauncher {
     if (!smem_attr(fast::k_stem_bwd_a, smem_a) || !smem_attr(fast::k_stem_bwd_b, smem_b)) return true;
     fast::StemBwdParams q{latent, x0, a0, g1, w.igdn_beta, w.igdn_gamma, w.conv0_w, w.up0_w, partial, g_latent,
                           n, d.ch, d.c0, d.c1, gw ? 1 : 0};
-    fast::k_stem_bwd_a<<<n * d.c0, 256, smem_a, st>>>(q, gy0);
+    nvf_launch(fast::k_stem_bwd_a, dim3(n * d.c0), dim3(256), (size_t)(smem_a), st, q, gy0);
     post();
-    fast::k_stem_bwd_b<<<n, 256, smem_b, st>>>(q, gy0);
+    nvf_launch(fast::k_stem_bwd_b, dim3(n), dim3(256), (size_t)(smem_b), st, q, gy0);
     post();
     if (gw) {
       const int n0 = d.c0 * d.c1 * 125, ng = d.c0 * d.c0, nu = d.ch * d.c0 * 125;
@@ -535,7 +576,7 @@ struct DevLauncher {
     float* partial = take_partial((size_t)ip.n * (ip.C * ip.C + ip.C));
     if (!partial) return false;
     fast::IgdnParamParams q{ip.x, ip.g, ip.beta, ip.gamma, partial, ip.n, ip.C};
-    fast::k_igdn_param<<<ip.n, 256, ip.C * 64 * 2 * sizeof(float), st>>>(q);
+    nvf_launch(fast::k_igdn_param, dim3(ip.n), dim3(256), (size_t)(ip.C * 64 * 2 * sizeof(float)), st, q);
     post();
     add_reduce(fast::ReduceJob{partial, ip.dgamma, ip.dbeta, ip.n, ip.C * ip.C + ip.C, ip.C * ip.C, ip.C, 0, 0});
     return true;
@@ -684,9 +725,9 @@ int nvf_param_prep(const NvfDesc* desc, const NvfParamSet* params, int q, const 
   pp.noise = noise; pp.q = q;
   pp.partial = (float*)workspace; pp.net_bits = net_bits;
   pp.beta_bound = beta_bound; pp.gamma_bound = gamma_bound; pp.pedestal = pedestal;
-  fast::k_param_prep<false><<<pp.total_chunks + 1, 256, 0, l.st>>>(pp);
+  nvf_launch(fast::k_param_prep<false>, dim3(pp.total_chunks + 1), dim3(256), (size_t)(0), l.st, pp);
   l.post();
-  fast::k_param_final<false><<<1, 32, 0, l.st>>>(pp);
+  nvf_launch(fast::k_param_final<false>, dim3(1), dim3(32), (size_t)(0), l.st, pp);
   l.post();
   return l.rc;
 }
@@ -719,9 +760,9 @@ int nvf_param_prep_backward(const NvfDesc* desc, const NvfParamSet* params, floa
   pp.partial = (float*)workspace;
   pp.g_sigma = out->lik_sigma; pp.g_mu = out->lik_mu;
   pp.beta_bound = beta_bound; pp.gamma_bound = gamma_bound;
-  fast::k_param_prep<true><<<pp.total_chunks + 1, 256, 0, l.st>>>(pp);
+  nvf_launch(fast::k_param_prep<true>, dim3(pp.total_chunks + 1), dim3(256), (size_t)(0), l.st, pp);
   l.post();
-  fast::k_param_final<true><<<1, 32, 0, l.st>>>(pp);
+  nvf_launch(fast::k_param_final<true>, dim3(1), dim3(32), (size_t)(0), l.st, pp);
   l.post();
   return l.rc;
 }
@@ -733,8 +774,8 @@ template <int CH>
 int latent_launch(DevLauncher& l, fast::LatentKParams& kp, bool bwd) {
   int grid = (int)(((int64_t)kp.n * 8 + fast::kLatentThreads - 1) / fast::kLatentThreads);
   if (grid > fast::kLatentMaxCtas) grid = fast::kLatentMaxCtas;
-  if (bwd) fast::k_latent_bwd<CH><<<grid, fast::kLatentThreads, 0, l.st>>>(kp);
-  else fast::k_latent_fwd<CH><<<grid, fast::kLatentThreads, 0, l.st>>>(kp);
+  if (bwd) nvf_launch(fast::k_latent_bwd<CH>, dim3(grid), dim3(fast::kLatentThreads), (size_t)(0), l.st, kp);
+  else nvf_launch(fast::k_latent_fwd<CH>, dim3(grid), dim3(fast::kLatentThreads), (size_t)(0), l.st, kp);
   l.post();
   return l.rc;
 }
@@ -802,7 +843,7 @@ int nvf_rd_total(const double* sums, const float* latent_bits, const float* net_
   p.sums = sums; p.latent_bits = latent_bits; p.net_bits = net_bits; p.n_pts = n_pts;
   p.n_total = n_total; p.lmbda = lmbda; p.w1 = w1; p.w2 = w2;
   p.loss = loss_out; p.stats = stats_out;
-  fast::k_rd_total<false><<<1, 32, 0, l.st>>>(p);
+  nvf_launch(fast::k_rd_total<false>, dim3(1), dim3(32), (size_t)(0), l.st, p);
   l.post();
   return l.rc;
 }
@@ -815,7 +856,7 @@ int nvf_rd_total_backward(const float* g_loss, const float* n_pts, float n_total
   fast::RdTotalParams p{};
   p.g_loss = g_loss; p.n_pts = n_pts; p.n_total = n_total; p.lmbda = lmbda; p.w1 = w1; p.w2 = w2;
   p.g_dist = g_dist; p.g_latent_bits = g_latent_bits; p.g_net_bits = g_net_bits;
-  fast::k_rd_total<true><<<1, 32, 0, l.st>>>(p);
+  nvf_launch(fast::k_rd_total<true>, dim3(1), dim3(32), (size_t)(0), l.st, p);
   l.post();
   return l.rc;
 }
@@ -828,9 +869,9 @@ int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   fast::AdamParams p{param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, n};
   int grid = (int)((n + 255) / 256);
   if (grid > l.n_sms * 4) grid = l.n_sms * 4;
-  fast::k_adam<<<grid, 256, 0, l.st>>>(p);
+  nvf_launch(fast::k_adam, dim3(grid), dim3(256), (size_t)(0), l.st, p);
   l.post();
-  fast::k_adam_tick<<<1, 1, 0, l.st>>>(step);
+  nvf_launch(fast::k_adam_tick, dim3(1), dim3(1), (size_t)(0), l.st, step);
   l.post();
   return l.rc;
 }
@@ -840,7 +881,7 @@ int nvf_ffma_microbench(int variant, int64_t iters, float* sink, double* flops_o
   DevLauncher l{(cudaStream_t)stream};
   if (l.init() != NVF_OK) return l.rc;
   const int grid = l.n_sms * 4;
-  k_ffma<<<grid, kThreads, 0, l.st>>>(variant, (long long)iters, sink);
+  nvf_launch(k_ffma, dim3(grid), dim3(kThreads), (size_t)(0), l.st, variant, (long long)iters, sink);
   l.post();
   if (flops_out) *flops_out = 2.0 * 256.0 * (double)iters * (double)grid * kThreads;
   return l.rc;

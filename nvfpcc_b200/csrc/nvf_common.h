@@ -120,6 +120,18 @@ NVF_HD void p2_load_w8(const float* wp, p2 (&w)[4]) {
   p2_ld2(wp + 4, w[2], w[3]);
 }
 
+// Programmatic dependent launch: first statement of every kernel.  Lets the NEXT kernel of the stream start
+// being scheduled as soon as all CTAs of this one are resident, then waits until the PREVIOUS kernel has
+// completed and its writes are visible (no-ops when the kernel was launched without the PDL attribute).
+#if defined(__CUDA_ARCH__)
+NVF_D void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#else
+inline void pdl_entry() {}
+#endif
+
 NVF_HD float relu(float v) { return v > 0.f ? v : 0.f; }
 // torch.sigmoid in fp32: 1/(1+exp(-x))
 NVF_HD float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }

@@ -161,6 +161,7 @@ __device__ __forceinline__ void conv_s1_chunk(const float* __restrict__ s_in, co
 template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA>
 __global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC>::THREADS, MINB)
     k_conv_s1(const __grid_constant__ CUtensorMap tmap, ConvS1Params p) {
+  pdl_entry();
   constexpr int XSH = TMA ? (4 - PAD % 4) % 4 : 0;
   using G = ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC, XSH>;
   constexpr int COT = G::COT;
@@ -371,6 +372,7 @@ struct WgradS1Cfg {
 
 template <int C, int DG, int TYG, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wgrad4_s1(WgradS1Params p) {
+  pdl_entry();
   using G = WgradS1Cfg<C, DG, TYG>;
   extern __shared__ __align__(128) float smem[];
   float* s_a = smem;
@@ -532,6 +534,7 @@ struct ReduceParams {
 };
 // grid.y = job; 8 lanes along the partial index x 32 outputs per CTA
 __global__ void __launch_bounds__(256) k_reduce_partials(ReduceParams p) {
+  pdl_entry();
   __shared__ float sm[8][33];
   const ReduceJob& J = p.job[blockIdx.y];
   const int n = J.n_w + J.n_b;

@@ -45,6 +45,7 @@ struct ConvTFwdCfg {
 
 template <int CI, int CO, int DIN, int MINB>
 __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_convT5_fwd(ConvTFwdParams p) {
+  pdl_entry();
   using G = ConvTFwdCfg<CI, CO, DIN>;
   extern __shared__ __align__(128) float smem[];
   float* s_in = smem;
@@ -204,6 +205,7 @@ struct ConvTDgradCfg {
 
 template <int CG, int CX, int DIN, int TY, int CGC, int MINB>
 __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, MINB) k_convT5_dgrad(ConvTDgradParams p) {
+  pdl_entry();
   using G = ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
   extern __shared__ __align__(128) float smem[];
   float* s_g = smem;
@@ -367,6 +369,7 @@ struct ConvTWgradCfg {
 
 template <int CI, int CO, int DIN, int TYB, int CIB, int MINB>
 __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) {
+  pdl_entry();
   using G = ConvTWgradCfg<CI, CO, DIN, TYB, CIB>;
   extern __shared__ __align__(128) float smem[];
   float* s_g = smem;
@@ -468,6 +471,7 @@ struct ChanSumFastParams {
   int32_t n, C, D, P, ZCH;  // ZCH chunks along z
 };
 __global__ void __launch_bounds__(256) k_chansum_fast(ChanSumFastParams p) {
+  pdl_entry();
   __shared__ float sm[256];
   const int c = blockIdx.x % p.C;
   const int zc = (blockIdx.x / p.C) % p.ZCH;

@@ -132,6 +132,7 @@ __device__ __forceinline__ void latent_load_params(const LatentKParams& p, float
 
 template <int CH>
 __global__ void __launch_bounds__(kLatentThreads) k_latent_fwd(LatentKParams p) {
+  pdl_entry();
   __shared__ double sm[kLatentThreads / 32];
   float W[CH][CH], bias[CH], beta[CH], gamma[CH][CH];
   latent_load_params<CH>(p, W, bias, beta, gamma);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kLatentThreads) k_latent_fwd(LatentKParams p) 
 
 template <int CH>
 __global__ void __launch_bounds__(kLatentThreads) k_latent_bwd(LatentKParams p) {
+  pdl_entry();
   constexpr int NP = LatentCfg<CH>::NP_BWD;
   float W[CH][CH], bias[CH], beta[CH], gamma[CH][CH];
   latent_load_params<CH>(p, W, bias, beta, gamma);
@@ -289,6 +291,7 @@ struct RdTotalParams {
 
 template <bool BWD>
 __global__ void k_rd_total(RdTotalParams p) {
+  pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (!BWD) {
     const float bce = (float)p.sums[0], ms0 = (float)p.sums[1], ms1 = (float)p.sums[2];
@@ -327,6 +330,7 @@ struct AdamParams {
 };
 
 __global__ void __launch_bounds__(256) k_adam(AdamParams p) {
+  pdl_entry();
   // bias corrections in double, like the Python scalars of torch's (non-capturable) Adam
   const double t = (double)p.step[0] + 1.0;
   const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
@@ -342,7 +346,10 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams p) {
   }
 }
 // the counter is advanced by a separate one-thread launch so every CTA of k_adam sees the same t
-__global__ void k_adam_tick(float* step) { step[0] += 1.f; }
+__global__ void k_adam_tick(float* step) {
+  pdl_entry();
+  step[0] += 1.f;
+}
 
 }  // namespace fast
 }  // namespace nvf

@@ -55,6 +55,7 @@ __device__ __forceinline__ float cta_sum_256(float v, float* sm) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) k_param_prep(ParamPrepParams p) {
+  pdl_entry();
   __shared__ float sm[8];
   const int tid = threadIdx.x;
   if ((int)blockIdx.x == p.total_chunks) {
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) k_param_prep(ParamPrepParams p) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(32) k_param_final(ParamPrepParams p) {
+  pdl_entry();
   const int l = threadIdx.x;
   if (!BWD) {
     if (l < kNumQuant) {

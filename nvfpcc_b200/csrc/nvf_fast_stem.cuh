@@ -40,6 +40,7 @@ __device__ __forceinline__ int stem_tap_lo(int o) { return o & 1; }
 // grid = n * 8: CTA (b, zs) recomputes the tiny up0 + IGDN and produces conv0's output slice zs;
 // the conv0_cls head runs afterwards as a classifier kernel (nvf_fast_conv.cuh).
 __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
+  pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
   float* s_lat = smem;                 // [CH][8]
@@ -156,6 +157,7 @@ __host__ __device__ inline int stem_partial_floats(int CH, int C0, int C1) {
 //   conv0 wgrad rows dW[ci][:][:]  (per-block partial), the conv0 bias gradient (ci == 0),
 //   conv0 dgrad gy[b][ci][64] -> p.gy (global).
 __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_out) {
+  pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
   float* s_g1 = smem;                   // [C1][512]
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
 
 // Kernel B, grid = n: IGDN backward (dx, dbeta, dgamma), up0 wgrad / bias, d_latent.
 __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float* gy_in) {
+  pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
   float* s_x0 = smem;                   // [C0][64]
