@@ -333,14 +333,14 @@ struct DevLauncher {
     return chk(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
 
-  template <int K, int CI, int CO, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA = false>
+  template <int K, int CI, int CO, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA = false, int COTP = 0>
   bool conv_s1(const LayerParams& p) {
     constexpr int XSH = TMA ? (4 - PAD % 4) % 4 : 0;
     static_assert(XSH <= 1, "TMA tiles support PAD % 4 in {0, 3}");
-    using G = fast::ConvS1Cfg<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, XSH>;
+    using G = fast::ConvS1Cfg<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, XSH, COTP>;
     constexpr int SMEM = TMA ? G::SMEM_BYTES_TMA : G::SMEM_BYTES;
     static_assert(SMEM <= 227 * 1024, "conv_s1 smem");
-    auto* k = fast::k_conv_s1<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, MINB, TMA>;
+    auto* k = fast::k_conv_s1<K, CI, CO, DIN, PAD, XG, TY, NZP, CIC, MINB, TMA, COTP>;
     if (!smem_attr(k, SMEM)) return true;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -353,11 +353,11 @@ struct DevLauncher {
     post();
     return true;
   }
-  template <int CI, int CO, int DIN, int MINB>
+  template <int CI, int CO, int DIN, int MINB, int KS = 1>
   bool convT_fwd(const LayerParams& p) {
-    using G = fast::ConvTFwdCfg<CI, CO, DIN>;
+    using G = fast::ConvTFwdCfg<CI, CO, DIN, KS>;
     static_assert(G::SMEM_BYTES <= 227 * 1024, "convT fwd smem");
-    auto* k = fast::k_convT5_fwd<CI, CO, DIN, MINB>;
+    auto* k = fast::k_convT5_fwd<CI, CO, DIN, MINB, KS>;
     if (!smem_attr(k, G::SMEM_BYTES)) return true;
     fast::ConvTFwdParams q{p.in, p.out, p.Wp, p.bias, p.n};
     nvf_launch(k, dim3(p.n * G::DOUT), dim3(G::THREADS), (size_t)(G::SMEM_BYTES), st, q);
@@ -383,8 +383,8 @@ struct DevLauncher {
       if (p.CI == 8) {
         if (fwd && p.Din == 35) return conv_s1<4, 8, 8, 35, 0, 8, 16, 2, 2, 2, true>(p);
         if (dg && p.Din == 32) return conv_s1<4, 8, 8, 32, 3, 9, 12, 2, 2, 2, true>(p);
-        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 2, 4, true>(p);
-        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 2, 4, true>(p);
+        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 2, 4, true, 4>(p);
+        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 2, 4, true, 4>(p);
       } else if (p.CI == 16) {
         if (fwd && p.Din == 35) return conv_s1<4, 16, 16, 35, 0, 8, 16, 1, 4, 2>(p);
         if (dg && p.Din == 32) return conv_s1<4, 16, 16, 32, 3, 9, 12, 1, 4, 2>(p);
@@ -413,7 +413,7 @@ struct DevLauncher {
     }
     if (p.op == OP_CONVT && p.P == 0 && p.act == ACT_RELU && !p.add && !p.mask && !p.out2) {
       if (p.CI == 8 && p.CO == 8 && p.Din == 16) return convT_fwd<8, 8, 16, 2>(p);
-      if (p.CI == 16 && p.CO == 8 && p.Din == 8) return convT_fwd<16, 8, 8, 2>(p);
+      if (p.CI == 16 && p.CO == 8 && p.Din == 8) return convT_fwd<16, 8, 8, 2, 4>(p);
       if (p.CI == 16 && p.CO == 16 && p.Din == 16) return convT_fwd<16, 16, 16, 1>(p);
       if (p.CI == 32 && p.CO == 16 && p.Din == 8) return convT_fwd<32, 16, 8, 1>(p);
       return false;

@@ -33,9 +33,10 @@ struct ConvS1Params {
 // XSH: extra left shift of the staged columns (tile column = ix + PAD + XSH).  The TMA unit needs the
 // innermost start coordinate of a box to be 16-byte aligned (x0 = -(PAD + XSH) must be a multiple of 4:
 // probed on B200, scripts/probe/tma_probe.cu), so the PAD = 3 data-gradient tiles use XSH = 1.
-template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int XSH = 0>
+template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int XSH = 0, int COTP = 0>
 struct ConvS1Cfg {
-  static constexpr int COT = C >= 8 ? 8 : C;               // output channels per thread
+  // output channels per thread; COTP > 0 overrides (smaller tiles = more threads for the small layers)
+  static constexpr int COT = COTP > 0 ? COTP : (C >= 8 ? 8 : C);
   static constexpr int DOUT = DIN + 2 * PAD - (K - 1);
   static constexpr int IN_PITCH = (DIN + 3) / 4 * 4, OUT_PITCH = (DOUT + 3) / 4 * 4;
   static constexpr int NV = IN_PITCH / 4;                 // float4 per global input row
@@ -158,12 +159,12 @@ __device__ __forceinline__ void conv_s1_chunk(const float* __restrict__ s_in, co
 // TMA = true: the input tile is fetched by the TMA unit (cp.async.bulk.tensor.5d, out-of-bounds = conv halo =
 // zero fill) and the weight chunk by a 1-D bulk copy, double buffered behind two mbarriers, so chunk ch+1
 // streams in while the CTA computes on chunk ch.  TMA = false: cooperative register-staged copy (tmap unused).
-template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA>
-__global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC>::THREADS, MINB)
+template <int K, int CI, int C, int DIN, int PAD, int XG, int TY, int NZP, int CIC, int MINB, bool TMA, int COTP = 0>
+__global__ void __launch_bounds__(ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC, 0, COTP>::THREADS, MINB)
     k_conv_s1(const __grid_constant__ CUtensorMap tmap, ConvS1Params p) {
   pdl_entry();
   constexpr int XSH = TMA ? (4 - PAD % 4) % 4 : 0;
-  using G = ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC, XSH>;
+  using G = ConvS1Cfg<K, CI, C, DIN, PAD, XG, TY, NZP, CIC, XSH, COTP>;
   constexpr int COT = G::COT;
   extern __shared__ __align__(128) float smem[];
   float* s_in = smem;

@@ -26,32 +26,46 @@ struct ConvTFwdParams {
   int32_t n;
 };
 
-template <int CI, int CO, int DIN>
+// KS: split of the input-channel sum over KS thread groups (partial sums combined through shared memory in
+// fixed order) - the small up1 layer has too few outputs to occupy the GPU otherwise.
+template <int CI, int CO, int DIN, int KS = 1>
 struct ConvTFwdCfg {
   static constexpr int DOUT = 2 * DIN + 3;
   static constexpr int IN_PITCH = (DIN + 3) / 4 * 4, OUT_PITCH = (DOUT + 3) / 4 * 4;
   static constexpr int QX = (DOUT + 7) / 8;   // column groups of 8 outputs
   static constexpr int RG = (DOUT + 3) / 4;   // row groups of 4 (two (y, y+2) pairs each)
   static constexpr int COG = CO / 4;
-  static constexpr int THREADS_USED = QX * RG * 2 * COG;
-  static constexpr int THREADS = (THREADS_USED + 31) / 32 * 32;
+  static constexpr int THREADS_USED = QX * RG * 2 * COG;                 // per channel-split group
+  static constexpr int THREADS = (THREADS_USED * KS + 31) / 32 * 32;
   static constexpr int TR = DIN + 4;          // tile rows: iy = r - 2
   static constexpr int IP = 4 * QX + 4;       // tile cols: ix = c - 4
   static constexpr int IN_FLOATS = CI * 3 * TR * IP;
   static constexpr int W_FLOATS = CI * 3 * 25 * CO;
-  static constexpr int SMEM_BYTES = (IN_FLOATS + W_FLOATS) * 4;
-  static_assert(CO % 4 == 0 && DIN % 4 == 0 && 2 * RG + 2 <= TR && DIN + 4 <= IP, "convT fwd tiling");
+  static constexpr int RED_FLOATS = (KS - 1) * THREADS_USED * 64;
+  static constexpr int SMEM_FLOATS = (IN_FLOATS + W_FLOATS) > RED_FLOATS ? (IN_FLOATS + W_FLOATS) : RED_FLOATS;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+  static_assert(CO % 4 == 0 && DIN % 4 == 0 && 2 * RG + 2 <= TR && DIN + 4 <= IP && CI % KS == 0, "convT fwd tiling");
 };
 
-template <int CI, int CO, int DIN, int MINB>
-__global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_convT5_fwd(ConvTFwdParams p) {
+template <int CI, int CO, int DIN, int MINB, int KS = 1>
+__global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN, KS>::THREADS, MINB) k_convT5_fwd(ConvTFwdParams p) {
   pdl_entry();
-  using G = ConvTFwdCfg<CI, CO, DIN>;
+  using G = ConvTFwdCfg<CI, CO, DIN, KS>;
   extern __shared__ __align__(128) float smem[];
   float* s_in = smem;
   float* s_w = smem + G::IN_FLOATS;
   const int tid = threadIdx.x;
-  const int z = blockIdx.x % G::DOUT, b = blockIdx.x / G::DOUT;
+  // even output slices use three kz taps, odd ones two: schedule the heavy (even) slices of all blocks first
+  constexpr int NEV = (G::DOUT + 1) / 2, NOD = G::DOUT / 2;
+  int z, b;
+  if ((int)blockIdx.x < p.n * NEV) {
+    z = 2 * ((int)blockIdx.x % NEV);
+    b = (int)blockIdx.x / NEV;
+  } else {
+    const int i = (int)blockIdx.x - p.n * NEV;
+    z = 2 * (i % NOD) + 1;
+    b = i / NOD;
+  }
   const int pz = z & 1;
   const int NT = pz ? 2 : 3;  // kz = pz + 2t, input slice iz = (z - pz) / 2 - t
 
@@ -81,8 +95,10 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
     tma::cp_async_wait_all();
   }
   __syncthreads();
-  if (tid >= G::THREADS_USED) return;
-  int r = tid;
+  const bool active = tid < G::THREADS_USED * KS;
+  if (KS == 1 && !active) return;
+  const int kgrp = active ? tid / G::THREADS_USED : 0, local = tid - kgrp * G::THREADS_USED;
+  int r = active ? local : 0;
   const int q = r % G::QX; r /= G::QX;
   const int pr = r % (2 * G::RG); r /= (2 * G::RG);
   const int cog = r;
@@ -99,7 +115,7 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
       for (int j = 0; j < 8; ++j) acc2[a][c][j] = p2_bcast(0.f);
 
 #pragma unroll 1
-  for (int ci = 0; ci < CI; ++ci) {
+  for (int ci = kgrp * (CI / KS); ci < (active ? (kgrp + 1) * (CI / KS) : 0); ++ci) {
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
       // tile rows 2rg .. 2rg+3  (iy = 2rg-2 .. 2rg+1), columns 4q+2 .. 4q+7  (ix = 4q-2 .. 4q+3)
@@ -147,6 +163,32 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN>::THREADS, MINB) k_con
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[a][c][j] = (c & 1) ? p2_hi(acc2[a][c >> 1][j]) : p2_lo(acc2[a][c >> 1][j]);
+  if constexpr (KS > 1) {
+    // combine the channel-split groups: groups 1.. hand their sums to group 0 (fixed order)
+    __syncthreads();                       // every group is done reading the staged tile
+    float* red = smem;
+    if (active && kgrp > 0) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red[((kgrp - 1) * 64 + (a * 4 + c) * 8 + j) * G::THREADS_USED + local] = acc[a][c][j];
+    }
+    __syncthreads();
+    if (!active || kgrp > 0) return;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sacc = acc[a][c][j];
+#pragma unroll
+          for (int g2 = 0; g2 < KS - 1; ++g2) sacc += red[(g2 * 64 + (a * 4 + c) * 8 + j) * G::THREADS_USED + local];
+          acc[a][c][j] = sacc;
+        }
+  }
   // ---- epilogue: bias + ReLU, columns >= DOUT of a padded row are written as zero
   constexpr size_t out_cs = (size_t)G::DOUT * G::DOUT * G::OUT_PITCH;
 #pragma unroll
