@@ -383,8 +383,8 @@ struct DevLauncher {
       if (p.CI == 8) {
         if (fwd && p.Din == 35) return conv_s1<4, 8, 8, 35, 0, 8, 16, 2, 2, 2, true>(p);
         if (dg && p.Din == 32) return conv_s1<4, 8, 8, 32, 3, 9, 12, 2, 2, 2, true>(p);
-        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 2, 2, 4, true, 4>(p);
-        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 10, 2, 2, 4, true, 4>(p);
+        if (fwd && p.Din == 19) return conv_s1<4, 8, 8, 19, 0, 4, 8, 1, 2, 6, true, 4>(p);
+        if (dg && p.Din == 16) return conv_s1<4, 8, 8, 16, 3, 5, 5, 1, 2, 6, true, 4>(p);    // 640 small CTAs: balance over 148 SMs
       } else if (p.CI == 16) {
         if (fwd && p.Din == 35) return conv_s1<4, 16, 16, 35, 0, 8, 16, 1, 4, 2>(p);
         if (dg && p.Din == 32) return conv_s1<4, 16, 16, 32, 3, 9, 12, 1, 4, 2>(p);
