@@ -419,10 +419,10 @@ struct DevLauncher {
       return false;
     }
     if (p.op == OP_CORR_S2 && p.P == 0 && p.act == ACT_NONE && !p.bias && !p.out2) {
-      if (p.CI == 8 && p.CO == 8 && p.Dout == 16) return convT_dgrad<8, 8, 16, 16, 2, 2>(p);
-      if (p.CI == 8 && p.CO == 16 && p.Dout == 8) return convT_dgrad<8, 16, 8, 8, 2, 2>(p);
-      if (p.CI == 16 && p.CO == 16 && p.Dout == 16) return convT_dgrad<16, 16, 16, 16, 2, 1>(p);
-      if (p.CI == 16 && p.CO == 32 && p.Dout == 8) return convT_dgrad<16, 32, 8, 8, 2, 1>(p);
+      if (p.CI == 8 && p.CO == 8 && p.Dout == 16) return convT_dgrad<8, 8, 16, 16, 1, 2>(p);
+      if (p.CI == 8 && p.CO == 16 && p.Dout == 8) return convT_dgrad<8, 16, 8, 8, 1, 2>(p);
+      if (p.CI == 16 && p.CO == 16 && p.Dout == 16) return convT_dgrad<16, 16, 16, 16, 1, 1>(p);
+      if (p.CI == 16 && p.CO == 32 && p.Dout == 8) return convT_dgrad<16, 32, 8, 8, 1, 1>(p);
       return false;
     }
     return false;

@@ -239,7 +239,8 @@ struct ConvTDgradCfg {
   static constexpr int G_FLOATS = CGC * 5 * GR * GPS;
   static constexpr int W_FLOATS = CGC * 125 * CX;
   static constexpr int RED_FLOATS = 4 * POS * 64;           // kz groups 1..4 hand their sums to group 0
-  static constexpr int SMEM_FLOATS = (G_FLOATS + W_FLOATS) > RED_FLOATS ? (G_FLOATS + W_FLOATS) : RED_FLOATS;
+  static constexpr int STAGE = G_FLOATS + W_FLOATS;         // one of two cp.async stages
+  static constexpr int SMEM_FLOATS = 2 * STAGE > RED_FLOATS ? 2 * STAGE : RED_FLOATS;
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
   static constexpr int BANDS = DIN / TY;
   static_assert(DIN % 4 == 0 && DIN % TY == 0 && TY % 2 == 0 && CX % 8 == 0 && CG % CGC == 0, "convT dgrad tiling");
@@ -250,8 +251,6 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
   pdl_entry();
   using G = ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
   extern __shared__ __align__(128) float smem[];
-  float* s_g = smem;
-  float* s_w = smem + G::G_FLOATS;
   const int tid = threadIdx.x;
   int t = blockIdx.x;
   const int band = t % G::BANDS; t /= G::BANDS;
@@ -276,24 +275,33 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
       for (int j = 0; j < 4; ++j) acc2[a][c][j] = p2_bcast(0.f);
 
   const float* g_b = p.g + (size_t)b * CG * G::DG * G::DG * G::GP;
-  for (int c0 = 0; c0 < CG; c0 += CGC) {
-    __syncthreads();
-    {
-      constexpr int NV = G::GP / 4;
-      for (int i = tid; i < CGC * 5 * G::GR * NV; i += G::THREADS) {
-        int q = i;
-        const int cv = q % NV; q /= NV;
-        const int rr = q % G::GR; q /= G::GR;
-        const int s = q % 5; q /= 5;
-        const int c = q;
-        tma::cp_async16(s_g + ((c * 5 + s) * G::GR + rr) * G::GPS + 4 * cv,
-                        g_b + (((size_t)(c0 + c) * G::DG + 2 * z + s) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv);
-      }
-      const float* src = p.Wp + (size_t)c0 * 125 * CX;
-      for (int i = tid; i < G::W_FLOATS / 4; i += G::THREADS) tma::cp_async16(s_w + 4 * i, src + 4 * i);
-      tma::cp_async_wait_all();
+  // two-stage cp.async pipeline over chunks of CGC gradient channels: chunk c+1 streams in while chunk c is consumed
+  auto stage = [&](int chunk) {
+    float* sg = smem + (chunk & 1) * G::STAGE;
+    float* sw = sg + G::G_FLOATS;
+    const int c0 = chunk * CGC;
+    constexpr int NV = G::GP / 4;
+    for (int i = tid; i < CGC * 5 * G::GR * NV; i += G::THREADS) {
+      int q = i;
+      const int cv = q % NV; q /= NV;
+      const int rr = q % G::GR; q /= G::GR;
+      const int s5 = q % 5; q /= 5;
+      const int c = q;
+      tma::cp_async16(sg + ((c * 5 + s5) * G::GR + rr) * G::GPS + 4 * cv,
+                      g_b + (((size_t)(c0 + c) * G::DG + 2 * z + s5) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv);
     }
-    __syncthreads();
+    const float* src = p.Wp + (size_t)c0 * 125 * CX;
+    for (int i = tid; i < G::W_FLOATS / 4; i += G::THREADS) tma::cp_async16(sw + 4 * i, src + 4 * i);
+  };
+  constexpr int NCHUNK = CG / CGC;
+  stage(0);
+  tma::cp_async_wait_all();
+  __syncthreads();
+#pragma unroll 1
+  for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+    if (chunk + 1 < NCHUNK) stage(chunk + 1);
+    const float* s_g = smem + (chunk & 1) * G::STAGE;
+    const float* s_w = s_g + G::G_FLOATS;
     if (active) {
 #pragma unroll 1
       for (int c = 0; c < CGC; ++c) {
@@ -326,6 +334,8 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
         }
       }
     }
+    tma::cp_async_wait_all();
+    __syncthreads();   // next chunk has landed; everyone is done with this one
   }
   float acc[2][8][4];
 #pragma unroll
