@@ -16,8 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnvf_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]           # IEEE arithmetic: --use_fast_math is never passed
+UNITS = ("nvf_capi.cu", "nvf_prep.cu")       # translation units of the one shared library
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _nvcc() -> str:
@@ -29,7 +31,8 @@ def _nvcc() -> str:
 
 def sources():
     deps = [os.path.join(ROOT, "include", "nvf_b200.h")]
-    deps += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cu", ".inl"))]
+    deps += [os.path.join(ROOT, "include", "nvf_prep_b200.h")]
+    deps += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cu", ".cuh", ".inl"))]
     return deps
 
 
@@ -43,9 +46,19 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "nvf_capi.cu")]
-    subprocess.check_call(cmd)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_unit(name: str) -> str:
+        obj = os.path.join(OBJ_DIR, name[:-3] + ".o")
+        subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, name)])
+        return obj
+
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(compile_unit, UNITS))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs)
     return OUT
 
 

@@ -14,6 +14,10 @@
 #include "nvf_fast_params.cuh"
 #include "nvf_fast_latent.cuh"
 
+namespace nvf {
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches); shared with nvf_prep.cu
+}
+
 using namespace nvf;
 
 namespace {
@@ -31,7 +35,6 @@ struct SidePool {
   bool ready = false;
 };
 SidePool g_side[kMaxDevices];
-std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
 
 
 // Optional programmatic stream serialisation (PDL), NVF_PDL=1: a kernel's CTAs may be scheduled while the
@@ -586,6 +589,10 @@ struct DevLauncher {
 }  // namespace
 
 // ------------------------------------------------------------------ C ABI
+namespace nvf {
+void note_cuda_error(int e) { g_last_cuda = e; }   // used by nvf_prep.cu
+}
+
 extern "C" {
 
 int nvf_abi_version(void) { return NVF_ABI_VERSION; }

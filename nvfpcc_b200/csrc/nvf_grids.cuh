@@ -1,0 +1,298 @@
+// Ground-truth occupancy grid + exact nearest-point distance field of the leaf
+// blocks (the training targets of the NVF path).  Replaces util_get_grids.py:19-46,
+// which asks an open3d KD-tree for the nearest cloud point of EVERY grid voxel
+// of every 32^3 leaf (N_leaf * 32768 Python calls) and stores
+//     dist[n,0,i,j,k]    = || nearest(p) - p ||,  p = origin[n] + (i,j,k)   (float64)
+//     gt_grid[n,0,i,j,k] = (dist == 0)                                     (uint8)
+//
+// Voxelised clouds live on the integer lattice, so the nearest-point distance
+// is an exact Euclidean distance transform of a binary volume:
+//   1. k_cells_insert / k_points_scatter: the cloud becomes a sparse set of
+//      32^3-bit occupancy cells (4 KB each, word (a0&31)*32+(a1&31), bit a2&31),
+//      found through an open-addressing hash of the cell coordinates.
+//   2. k_edt_blocks: one CTA per leaf block runs the separable squared-distance
+//      transform plane by plane: per plane a0', every non-empty row a1' gives
+//      g(a1',k) = distance along a2 to the nearest set bit (CLZ/FFS on a 64-bit
+//      window), h(j,k) = min_a1' g^2 + (j-a1')^2, and the block's 32^3 squared
+//      distances (u16 in shared memory) take min(d2, h + (i-a0')^2).
+//      A leaf holds at least one point, so every distance is <= 31*sqrt(3) < 54:
+//      the own 32 planes are swept first, then only the outer planes within
+//      floor(sqrt(max d2)) of the block.  Everything is integer arithmetic;
+//      dist = sqrt((double)d2) is correctly rounded, hence bit-identical to the
+//      float64 result of the reference (ties between equidistant points do not matter).
+//   No float atomics, no order dependence: results are deterministic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nvf_common.h"
+
+namespace nvf {
+namespace grids {
+
+constexpr int L = 32;                    // leaf edge
+constexpr int RMAX = 53;                 // floor(31 * sqrt(3)): farthest possible nearest point of a non-empty leaf
+constexpr int EXT = L + 2 * RMAX;        // 138 rows / planes / bits of the search window
+constexpr int NC = 6;                    // 32-cells per axis that can intersect the window (unaligned origins)
+constexpr int ROWW = NC + 4;             // row words: 2 zero words, 6 data words, 2 zero words
+constexpr int COFF = 1 << 20;            // cell coordinates are stored biased into 21 bits
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr uint32_t D2_INF = 0xFFFFu;
+
+enum { GRID_STATUS_CELL_OVERFLOW = 1, GRID_STATUS_NOT_FOUND = 2 };
+
+struct CellTable {
+  unsigned long long* keys;   // [cap] cell key or kEmptyKey
+  int32_t* vals;              // [cap] cell id or -1
+  uint32_t* masks;            // [max_cells][1024] occupancy words
+  int32_t* counter;           // [1] number of cells
+  int32_t* status;            // [1] GRID_STATUS_* bits
+  uint32_t cap_mask;          // cap - 1 (cap is a power of two)
+  int32_t max_cells;
+};
+
+__device__ __forceinline__ bool cell_key(int c0, int c1, int c2, unsigned long long& key) {
+  const int b0 = c0 + COFF, b1 = c1 + COFF, b2 = c2 + COFF;
+  if ((unsigned)b0 >= (2u * COFF) || (unsigned)b1 >= (2u * COFF) || (unsigned)b2 >= (2u * COFF)) return false;
+  key = ((unsigned long long)b0 << 42) | ((unsigned long long)b1 << 21) | (unsigned long long)b2;
+  return true;
+}
+__device__ __forceinline__ uint32_t cell_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+__device__ __forceinline__ int cell_lookup(const CellTable& T, int c0, int c1, int c2) {
+  unsigned long long key;
+  if (!cell_key(c0, c1, c2, key)) return -1;
+  uint32_t slot = cell_hash(key) & T.cap_mask;
+  for (uint32_t probe = 0; probe <= T.cap_mask; ++probe) {
+    const unsigned long long k = T.keys[slot];
+    if (k == key) return T.vals[slot];
+    if (k == kEmptyKey) return -1;
+    slot = (slot + 1) & T.cap_mask;
+  }
+  return -1;
+}
+
+// Pass 1a: every point claims the hash slot of its cell; the first claimant numbers the cell.
+__global__ void __launch_bounds__(256) k_cells_insert(const int32_t* __restrict__ pts, int64_t n, CellTable T) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long key;
+    if (!cell_key(pts[3 * i] >> 5, pts[3 * i + 1] >> 5, pts[3 * i + 2] >> 5, key)) {
+      atomicOr(T.status, GRID_STATUS_CELL_OVERFLOW);
+      continue;
+    }
+    uint32_t slot = cell_hash(key) & T.cap_mask;
+    for (uint32_t probe = 0; probe <= T.cap_mask; ++probe) {
+      const unsigned long long prev = atomicCAS(T.keys + slot, kEmptyKey, key);
+      if (prev == kEmptyKey) {
+        const int id = atomicAdd(T.counter, 1);
+        if (id < T.max_cells) {
+          T.vals[slot] = id;
+        } else {
+          T.vals[slot] = -1;
+          atomicOr(T.status, GRID_STATUS_CELL_OVERFLOW);
+        }
+        break;
+      }
+      if (prev == key) break;
+      slot = (slot + 1) & T.cap_mask;
+    }
+  }
+}
+
+// Pass 1b: set the point's bit in its cell.
+__global__ void __launch_bounds__(256) k_points_scatter(const int32_t* __restrict__ pts, int64_t n, CellTable T) {
+  pdl_entry();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a0 = pts[3 * i], a1 = pts[3 * i + 1], a2 = pts[3 * i + 2];
+    const int id = cell_lookup(T, a0 >> 5, a1 >> 5, a2 >> 5);
+    if (id >= 0) atomicOr(T.masks + (size_t)id * 1024 + (a0 & 31) * 32 + (a1 & 31), 1u << (a2 & 31));
+  }
+}
+
+struct EdtParams {
+  const int32_t* origins;   // [n][3]
+  uint8_t* gt;              // [n][32768] or null
+  double* dist64;           // [n][32768] or null
+  float* dist32;            // [n][32768] or null
+  uint16_t* d2;             // [n][32768] or null  (squared distance, 0xFFFF = nothing within max_radius)
+  int32_t max_radius;       // <= RMAX
+  CellTable T;
+};
+
+struct EdtSmem {
+  uint16_t d2[L * L * L];         // 64 KB running squared distances [i][j][k]
+  uint16_t g2[EXT][L];            // squared distance along a2 for the rows of the current plane
+  uint32_t rowbits[EXT][ROWW];    // bit window of every row of the current plane
+  int32_t cellid[NC][NC][NC];
+  int32_t slab_any[NC];
+  int32_t rowlist[EXT];
+  int32_t nrows;
+  uint32_t red[8];
+};
+
+// 64 window bits starting at bit position b of a row (b + 64 <= 32 * ROWW)
+__device__ __forceinline__ unsigned long long row_bits64(const uint32_t* row, int b) {
+  const int q = b >> 5, sh = b & 31;
+  const uint32_t w0 = row[q], w1 = row[q + 1], w2 = row[q + 2];
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// One plane a0 = o0 + prel of the window: fold it into the block's squared distances.
+// rlim: only rows / output slices within rlim of the block can still improve a distance.
+__device__ __forceinline__ void edt_plane(EdtSmem& S, const EdtParams& p, int o0, int o1, int cb0, int cb1, int xoff,
+                                          int prel, int rlim) {
+  const int tid = threadIdx.x;
+  const int a0 = o0 + prel;
+  const int cz = (a0 >> 5) - cb0;
+  if (!S.slab_any[cz]) return;                       // uniform: no cell in this slab of the window
+  // ---- (1) fetch the bit windows of the rows within rlim of the block
+  const int r_lo = RMAX - rlim, r_hi = RMAX + L - 1 + rlim;
+  for (int idx = tid; idx < EXT * NC; idx += kThreads) {
+    const int r = idx / NC, cx = idx - r * NC;
+    uint32_t w = 0;
+    if (r >= r_lo && r <= r_hi) {
+      const int a1 = o1 + r - RMAX;
+      const int cid = S.cellid[cz][(a1 >> 5) - cb1][cx];
+      if (cid >= 0) w = __ldg(p.T.masks + (size_t)cid * 1024 + (a0 & 31) * 32 + (a1 & 31));
+    }
+    S.rowbits[r][2 + cx] = w;
+  }
+  __syncthreads();
+  // ---- (2) ordered list of the non-empty rows (warp 0)
+  if (tid < 32) {
+    int base = 0;
+    for (int it = 0; it < (EXT + 31) / 32; ++it) {
+      const int r = it * 32 + tid;
+      bool ne = false;
+      if (r < EXT) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) o |= S.rowbits[r][2 + c];
+        ne = o != 0;
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, ne);
+      if (ne) S.rowlist[base + __popc(b & ((1u << tid) - 1u))] = r;
+      base += __popc(b);
+    }
+    if (tid == 0) S.nrows = base;
+  }
+  __syncthreads();
+  const int nrows = S.nrows;
+  if (nrows == 0) return;                            // uniform
+  // ---- (3) squared distance along a2 to the nearest set bit, for the 32 columns of the block
+  for (int idx = tid; idx < nrows * L; idx += kThreads) {
+    const int r = S.rowlist[idx >> 5], k = idx & 31;
+    const uint32_t* row = S.rowbits[r];
+    const int c = 64 + xoff + RMAX + k;              // bit position of column k in the padded row
+    const unsigned long long below = row_bits64(row, c - 63);   // bit 63 = position c
+    const unsigned long long above = row_bits64(row, c);        // bit 0 = position c
+    uint32_t g = 64;
+    if (below) g = (uint32_t)__clzll((long long)below);
+    if (above) g = min(g, (uint32_t)(__ffsll((long long)above) - 1));
+    S.g2[r][k] = g >= 64 ? (uint16_t)D2_INF : (uint16_t)(g * g);
+  }
+  __syncthreads();
+  // ---- (4) thread (k, 4 rows j): h = min over rows, then the slices i within rlim of the plane
+  const int k = tid & 31, j0 = (tid >> 5) * 4;
+  uint32_t h[4] = {1u << 20, 1u << 20, 1u << 20, 1u << 20};
+  for (int n = 0; n < nrows; ++n) {
+    const int r = S.rowlist[n];
+    const uint32_t v = S.g2[r][k];
+    const int dj = j0 - (r - RMAX);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) h[t] = min(h[t], v + (uint32_t)((dj + t) * (dj + t)));
+  }
+  const int i_lo = max(0, prel - rlim), i_hi = min(L - 1, prel + rlim);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (h[t] >= D2_INF) continue;
+    uint16_t* col = S.d2 + (j0 + t) * L + k;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const uint32_t cand = h[t] + (uint32_t)((i - prel) * (i - prel));
+      const uint32_t cur = col[i * L * L];
+      if (cand < cur) col[i * L * L] = (uint16_t)cand;
+    }
+  }
+  // no trailing barrier: the next plane's barriers order its writes after these reads (see file header)
+}
+
+__device__ __forceinline__ int isqrt_floor(uint32_t v) {
+  int r = (int)sqrtf((float)v);
+  while ((uint32_t)(r * r) > v) --r;
+  while ((uint32_t)((r + 1) * (r + 1)) <= v) ++r;
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
+  pdl_entry();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EdtSmem& S = *reinterpret_cast<EdtSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int n = blockIdx.x;
+  const int o0 = p.origins[3 * n], o1 = p.origins[3 * n + 1], o2 = p.origins[3 * n + 2];
+  const int cb0 = (o0 - RMAX) >> 5, cb1 = (o1 - RMAX) >> 5, cb2 = (o2 - RMAX) >> 5;
+  const int xoff = (o2 - RMAX) - 32 * cb2;           // bit offset of the window start in data word 0
+  // ---- setup: cells of the window, zero pad words, distances = infinity
+  if (tid < NC) S.slab_any[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < NC * NC * NC; i += kThreads) {
+    const int cx = i % NC, cy = (i / NC) % NC, cz = i / (NC * NC);
+    const int id = cell_lookup(p.T, cb0 + cz, cb1 + cy, cb2 + cx);
+    S.cellid[cz][cy][cx] = id;
+    if (id >= 0) S.slab_any[cz] = 1;
+  }
+  for (int r = tid; r < EXT; r += kThreads) {
+    S.rowbits[r][0] = 0; S.rowbits[r][1] = 0; S.rowbits[r][ROWW - 2] = 0; S.rowbits[r][ROWW - 1] = 0;
+  }
+  {
+    uint32_t* d = reinterpret_cast<uint32_t*>(S.d2);
+    for (int i = tid; i < L * L * L / 2; i += kThreads) d[i] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  const int R = min(max(p.max_radius, 0), RMAX);
+  // ---- own planes
+  for (int prel = 0; prel < L; ++prel) edt_plane(S, p, o0, o1, cb0, cb1, xoff, prel, R);
+  __syncthreads();
+  // ---- largest squared distance so far bounds the remaining search radius
+  uint32_t m = 0;
+  {
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(S.d2);
+    for (int i = tid; i < L * L * L / 2; i += kThreads) {
+      const uint32_t v = d[i];
+      m = max(m, max(v & 0xFFFFu, v >> 16));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) S.red[tid >> 5] = m;
+  }
+  __syncthreads();
+  m = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) m = max(m, S.red[w]);
+  const int rlim = m >= D2_INF ? R : min(R, isqrt_floor(m));
+  // ---- outer planes, nearest first
+  for (int dz = 1; dz <= rlim; ++dz) {
+    edt_plane(S, p, o0, o1, cb0, cb1, xoff, -dz, rlim);
+    edt_plane(S, p, o0, o1, cb0, cb1, xoff, L - 1 + dz, rlim);
+  }
+  __syncthreads();
+  // ---- outputs
+  const size_t base = (size_t)n * (L * L * L);
+  bool missing = false;
+  for (int i = tid; i < L * L * L; i += kThreads) {
+    const uint32_t v = S.d2[i];
+    missing |= v >= D2_INF;
+    const double d = v >= D2_INF ? __longlong_as_double(0x7ff0000000000000ll) : sqrt((double)v);
+    if (p.gt) p.gt[base + i] = v == 0 ? 1 : 0;
+    if (p.dist64) p.dist64[base + i] = d;
+    if (p.dist32) p.dist32[base + i] = (float)d;
+    if (p.d2) p.d2[base + i] = (uint16_t)v;
+  }
+  if (missing) atomicOr(p.T.status, GRID_STATUS_NOT_FOUND);
+}
+
+}  // namespace grids
+}  // namespace nvf

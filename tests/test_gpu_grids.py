@@ -1,0 +1,110 @@
+"""GPU parity of nvf_build_grids (include/nvf_prep_b200.h) against the oracle and against the
+fixture written by the unmodified reference script: distances are float64 and must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grids_oracle as GO
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(points, origins, **kw):
+    from nvfpcc_b200 import grids
+    r = grids.build_grids(points, origins, want_gt=True, want_dist64=True, want_dist32=True, want_d2=True, **kw)
+    return {k: v.cpu().numpy() for k, v in r.items()}
+
+
+def assert_exact(r, gt_ref, dist_ref):
+    assert r["dist"].dtype == np.float64 and r["gt"].dtype == np.uint8
+    assert np.array_equal(r["dist"], dist_ref)
+    assert np.array_equal(r["gt"], gt_ref)
+    assert np.array_equal(r["dist32"], dist_ref.astype(np.float32))       # utils/dataloader.py:171 .float()
+    assert np.array_equal(r["d2"].astype(np.int64).reshape(dist_ref.shape), np.rint(dist_ref ** 2).astype(np.int64))
+
+
+def test_matches_reference_script_fixture():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "grids_small.npz"))
+    n = g["origins"].shape[0]
+    dist_ref = np.sqrt(g["d2"].astype(np.float64)).reshape(n, 1, 32, 32, 32)
+    gt_ref = np.unpackbits(g["gt"])[: n * 32768].reshape(n, 1, 32, 32, 32)
+    r = run(g["points"], g["origins"], max_cells=256)
+    assert_exact(r, gt_ref, dist_ref)
+
+
+def test_sphere_shell_all_leaves_match_oracle():
+    from nvfpcc_b200 import synth
+    pts = synth.sphere_shell_points(256)
+    origins = synth.leaf_origins(pts)
+    gt_ref, dist_ref = GO.build_grids(pts, origins, workers=-1)
+    r = run(pts, origins)
+    assert_exact(r, gt_ref, dist_ref)
+    assert int(r["gt"].sum()) == pts.shape[0]                              # every point lands in exactly one leaf
+    r2 = run(pts, origins)
+    assert all(np.array_equal(r[k], r2[k]) for k in r)                     # deterministic
+
+
+def test_unaligned_and_negative_origins():
+    rng = np.random.default_rng(3)
+    pts = np.unique(rng.integers(-70, 120, size=(4000, 3)), axis=0).astype(np.int32)
+    origins = np.array([[-37, 5, 11], [0, 0, 0], [13, -64, 50], [77, 81, -3], [-70, -70, -70]], dtype=np.int32)
+    # every leaf must hold a point for the exact-radius guarantee: add one inside each
+    pts = np.unique(np.concatenate([pts, origins + rng.integers(0, 32, size=origins.shape)], 0), axis=0).astype(np.int32)
+    gt_ref, dist_ref = GO.build_grids(pts, origins)
+    r = run(pts, origins, max_cells=1024)
+    assert_exact(r, gt_ref, dist_ref)
+
+
+def test_single_point_leaf_reaches_the_full_diagonal():
+    # one voxel in the far corner of its leaf; the only other points are farther than the leaf diagonal
+    pts = np.array([[31, 31, 31], [200, 0, 0], [0, 200, 0]], dtype=np.int32)
+    origins = np.array([[0, 0, 0]], dtype=np.int32)
+    gt_ref, dist_ref = GO.build_grids(pts, origins)
+    r = run(pts, origins)
+    assert_exact(r, gt_ref, dist_ref)
+    assert r["dist"][0, 0, 0, 0, 0] == np.sqrt(3 * 31 * 31)
+    # nearer points in neighbouring cells on every side win over the own point
+    pts2 = np.concatenate([pts, [[-1, 0, 0], [0, -2, 5], [3, 3, -3], [32, 31, 31], [16, 40, 16]]]).astype(np.int32)
+    gt_ref, dist_ref = GO.build_grids(pts2, origins)
+    assert_exact(run(pts2, origins), gt_ref, dist_ref)
+
+
+def test_dense_and_sparse_random_leaves():
+    rng = np.random.default_rng(11)
+    dense = rng.integers(0, 64, size=(60000, 3))
+    sparse = rng.integers(64, 192, size=(60, 3))
+    pts = np.unique(np.concatenate([dense, sparse], 0), axis=0).astype(np.int32)
+    origins = (np.unique(pts // 32, axis=0) * 32).astype(np.int32)
+    gt_ref, dist_ref = GO.build_grids(pts, origins)
+    assert_exact(run(pts, origins), gt_ref, dist_ref)
+
+
+def test_status_flags_raise():
+    from nvfpcc_b200 import _lib, grids
+    pts = np.array([[5, 5, 5]], dtype=np.int32)
+    with pytest.raises(_lib.NvfError, match="no cloud point"):
+        grids.build_grids(pts, np.array([[320, 320, 320]], dtype=np.int32))          # empty leaf, nothing in reach
+    many = (np.arange(300)[:, None] * np.array([[32, 0, 0]])).astype(np.int32)
+    with pytest.raises(_lib.NvfError, match="max_cells"):
+        grids.build_grids(many, many[:2], max_cells=64)
+    r = grids.build_grids(pts, np.array([[320, 320, 320]], dtype=np.int32), check=False, want_d2=True)
+    assert int(r["status"].item()) == grids.STATUS_NOT_FOUND and bool(torch.isinf(r["dist"]).all())
+
+
+def test_cli_writes_the_reference_files(tmp_path, monkeypatch):
+    from nvfpcc_b200 import grids, synth
+    pts = synth.sphere_shell_points(128)
+    origins = synth.leaf_origins(pts)
+    monkeypatch.chdir(tmp_path)
+    with open("cloud.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nend_header\n" % len(pts))
+        np.savetxt(f, pts, fmt="%d")
+    np.savetxt("cloud_l5_origins.txt", origins, delimiter=",", fmt="%d")
+    assert grids.main(["grids", "sub/dir/../../cloud.ply".replace("sub/dir/../../", ""), "5"]) == 0
+    gt, dist, org = np.load("cloud_l5_gt_grid.npy"), np.load("cloud_l5_dist.npy"), np.load("cloud_l5_origins.npy")
+    assert gt.dtype == np.uint8 and dist.dtype == np.float64 and org.dtype == np.float64
+    gt_ref, dist_ref = GO.build_grids(pts, origins)
+    assert np.array_equal(gt, gt_ref) and np.array_equal(dist, dist_ref) and np.array_equal(org, origins)
