@@ -44,7 +44,8 @@ enum {
   NVF_ERR_UNSUPPORTED = -2,  /* channel configuration not compiled in       */
   NVF_ERR_WORKSPACE = -3,    /* workspace too small                         */
   NVF_ERR_CUDA = -4,         /* a CUDA runtime call failed (see nvf_last_cuda_error) */
-  NVF_ERR_NO_DEVICE = -5     /* no sm_100 device / kernel image not loadable */
+  NVF_ERR_NO_DEVICE = -5,    /* no sm_100 device / kernel image not loadable */
+  NVF_ERR_BITSTREAM = -6     /* corrupt or truncated entropy-coded stream (nvf_prep_b200.h) */
 };
 
 /* Decoder geometry: latent channels `ch`, chanstr c0,c1,c2,c3

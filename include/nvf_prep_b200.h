@@ -48,6 +48,39 @@ int nvf_build_grids(const int32_t* points, int64_t n_points, const int32_t* orig
                     int64_t max_cells, int32_t max_radius, uint8_t* gt_out, double* dist64_out, float* dist32_out,
                     uint16_t* d2_out, int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Latent bitstream: the arithmetic code of the rounded latents.  Replaces the
+ * `./module_arithmeticcoding e|d 1 1` subprocess of encode()/decode() (NVFPCC.py:446-477,
+ * 588-607; module_arithmeticcoding.cpp:368-432) with an in-process call producing / consuming
+ * the SAME byte stream (`latent_pack['latent_byte_stream']`).  HOST pointers throughout.
+ *   symbols  [n] int16 in [0, 1024]: latent + 512 (NVFPCC.py:447,453)
+ *   mu,sigma [n] float32 per-symbol Gaussian parameters (mu already offset by 512, :455-460)
+ *   level1/2 number of low mantissa bits cleared in mu / sigma (the helper's argv[2], argv[3]; 1 and 1)
+ *   out      capacity out_cap >= nvf_arith_encode_bound(n); *out_len = bytes written
+ * nvf_arith_decode_host returns NVF_ERR_BITSTREAM when the stream cannot have been produced
+ * with these parameters (the reference helper asserts in that case).
+ */
+int nvf_arith_encode_bound(int64_t n_symbols, size_t* bytes_out);
+int nvf_arith_encode_host(const int16_t* symbols, const float* mu, const float* sigma, int64_t n, int level1,
+                          int level2, uint8_t* out, size_t out_cap, size_t* out_len);
+int nvf_arith_decode_host(const uint8_t* stream, size_t stream_len, const float* mu, const float* sigma, int64_t n,
+                          int level1, int level2, int16_t* symbols_out);
+
+/*
+ * Weight bitstream: Huffman code of the 1/16-quantised kernels.  Replaces entropy_encode /
+ * entropy_decode of util_code_quantized_weights.py:108-148 (a Python walk over a '0'/'1'
+ * string, one slice per bit) for the codebook carried in the pack (`inv_codebook`).  HOST pointers.
+ *   code_symbols [n_codes] int32, code_lengths [n_codes] (<= 64), code_bits [n_codes] codeword
+ *   value, first bit of the codeword = most significant of its `length` bits; stream bits are
+ *   packed MSB first and zero padded to a byte boundary.
+ */
+int nvf_huffman_encode_host(const int32_t* symbols, int64_t n, const int32_t* code_symbols,
+                            const uint8_t* code_lengths, const uint64_t* code_bits, int32_t n_codes, uint8_t* out,
+                            size_t out_cap, size_t* out_len);
+int nvf_huffman_decode_host(const uint8_t* stream, size_t stream_len, const int32_t* code_symbols,
+                            const uint8_t* code_lengths, const uint64_t* code_bits, int32_t n_codes,
+                            int64_t n_symbols, int32_t* symbols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnvf_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]           # IEEE arithmetic: --use_fast_math is never passed
-UNITS = ("nvf_capi.cu", "nvf_prep.cu")       # translation units of the one shared library
+UNITS = ("nvf_capi.cu", "nvf_prep.cu", "nvf_entropy.cpp")       # translation units of the one shared library
 OBJ_DIR = os.path.join(HERE, "build")
 
 
@@ -32,7 +32,7 @@ def _nvcc() -> str:
 def sources():
     deps = [os.path.join(ROOT, "include", "nvf_b200.h")]
     deps += [os.path.join(ROOT, "include", "nvf_prep_b200.h")]
-    deps += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cu", ".cuh", ".inl"))]
+    deps += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cu", ".cuh", ".cpp", ".inl"))]
     return deps
 
 
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_unit(name: str) -> str:
-        obj = os.path.join(OBJ_DIR, name[:-3] + ".o")
+        obj = os.path.join(OBJ_DIR, os.path.splitext(name)[0] + ".o")
         subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, name)])
         return obj
 

@@ -605,6 +605,7 @@ const char* nvf_strerror(int code) {
     case NVF_ERR_WORKSPACE: return "workspace too small";
     case NVF_ERR_CUDA: return "CUDA runtime error";
     case NVF_ERR_NO_DEVICE: return "no sm_100 device";
+    case NVF_ERR_BITSTREAM: return "corrupt entropy-coded stream";
     default: return "unknown error";
   }
 }
