@@ -24,3 +24,12 @@ def golden_A():
 def golden_B():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "nvf_B.npz"))
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """The product binding on a CUDA device (the `-m gpu` tier)."""
+    import torch
+    from nvfpcc_b200 import _lib
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return _lib.cuda_binding()

@@ -120,3 +120,45 @@ def test_single_symbol_alphabet():
     stream, shapes = entropy.entropy_encode(pool, codebook)
     assert stream == b"" and inv == {"": 0}
     assert np.array_equal(entropy.entropy_decode(stream, inv, 6, shapes)[0], pool[0])
+
+
+REF_ROOT = os.environ.get("NVF_REFERENCE_ROOT", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF_ROOT, "util_code_quantized_weights.py")),
+                    reason="reference checkout absent")
+def test_reference_module_decodes_our_weight_pack():
+    """The pack written here is readable by the reference's own entropy_decode (util_code_quantized_weights.py:130-148)."""
+    import sys
+    from oracle.gen_golden_entropy import bitstream_stub
+    from nvfpcc_b200 import network, synth
+    sys.modules.setdefault("bitstream", bitstream_stub())
+    sys.path.insert(0, REF_ROOT)
+    try:
+        import util_code_quantized_weights as U
+    finally:
+        sys.path.remove(REF_ROOT)
+    network.set_seed(synth.synthetic_seed())
+    net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8")
+    sd = synth.random_kernel_deltas({k: v.clone() for k, v in net.state_dict().items()}, quantize=True)
+    pack = entropy.enc_dec_from_state(sd)
+    dec = U.entropy_decode(pack["bit_stream"], pack["inv_codebook"], pack["element_length"], pack["shape_list"])
+    for k, v in zip(pack["keys_quantize"], dec):
+        assert np.array_equal(v / 16, sd[k].numpy()), k
+    assert U.keys_quantize == entropy.keys_quantize and U.keys_code_as_is == entropy.keys_code_as_is and U.qp == entropy.qp
+
+
+def test_quantize_state_and_ply_writer(tmp_path):
+    from nvfpcc_b200 import codec, grids, network, synth
+    network.set_seed(synth.synthetic_seed())
+    net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8")
+    sd = synth.random_kernel_deltas({k: v.clone() for k, v in net.state_dict().items()}, quantize=False)
+    q = codec.quantize_state(sd, 16)
+    assert not any(("conv1_cls" in k or "conv0_cls" in k) for k in q)                 # manipulate_weights.py drops the aux heads
+    for k in entropy.keys_quantize:
+        assert torch.equal(q[k], torch.round(sd[k] * 16) / 16)
+    assert torch.equal(q["reconstructor.conv2.b"], sd["reconstructor.conv2.b"])
+    entropy.enc_dec_from_state(q)                                                       # discrete -> codable
+    pts = np.array([[1, 2, 3], [1023, 0, 77]], dtype=np.int32)
+    codec.write_ply_ascii(str(tmp_path / "a.ply"), pts)
+    assert np.array_equal(grids.read_ply_xyz(str(tmp_path / "a.ply")), pts.astype(np.float64))
