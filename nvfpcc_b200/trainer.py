@@ -304,3 +304,103 @@ class EmbeddingStep:
                 p.requires_grad_(r)
         self.opt.step()
         return stats
+
+
+def dataset_index(i: int, n_leaf: int, shuffle: bool = True) -> int:
+    """LoadedVoxelDataset.__getitem__ (utils/dataloader.py:163-167): the 'shuffle' of the reference's
+    dataset is the fixed stride permutation (i * 2113) % N_leaf."""
+    return (i * 2113) % n_leaf if shuffle else i
+
+
+def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: int, lr: float, lmbda: float,
+        w1: float = 1.0, w2: float = 1.0, wemb: float = 5.0, phase_change: int = 100, focal_alpha: float = 0.9,
+        emb: Optional[torch.Tensor] = None, n_total: Optional[float] = None, start_epoch: int = 0,
+        milestones=(300, 400, 450), checkpoint_dir: Optional[str] = None, save_every: int = 10,
+        dataset_shuffle: bool = True, use_graph: bool = True, log=None):
+    """The epoch loop of train() (NVFPCC.py:103-296) on the sync-free steps above.
+
+    gt / dist_: the whole dataset, [N_leaf,1,32,32,32] (uint8 / float, host or device) - kept resident
+    in HBM (vox10: 1247 x 256 KB = 0.33 GB), so the weight loop has no H2D traffic.
+    Per epoch: the weight loop over all leaves at `batchsize` (drop_last=False; the short last batch
+    wraps around to keep the captured graph's shapes - it repeats leaves of the first batch), then ONE
+    full-batch embedding update, then both schedulers step on the WEIGHT optimizer (NVFPCC.py:126:
+    sch_emb wraps `opt`, so the weight LR decays by 0.01 per milestone and the embedding LR never decays).
+    Under torch.distributed each rank owns a contiguous range of leaves (embedding rows, gt/dist shards);
+    its minibatches come from that range and the shared-weight gradient is all-reduced once per step.
+    Checkpoints are the reference's files: '%04d.ckpt' (state_dict) and '%04d_emb.ckpt' (the embedding tensor).
+    Returns (emb, history) where history[e] holds the epoch means of STAT_NAMES (one D2H read per epoch)."""
+    import os
+    import warnings
+
+    dev = next(net.parameters()).device
+    if dev.type != "cuda":
+        raise ops.NvfError("trainer.fit needs the network on a CUDA device; there is no CPU fallback")
+    rank, ws = D.world()
+    n_leaf_all = int(gt.shape[0])
+    lo, hi = D.block_range(n_leaf_all, rank, ws)
+    gt_d = gt[lo:hi].to(dev, torch.float32)
+    dist_d = dist_[lo:hi].to(dev, torch.float32)
+    n_leaf = hi - lo
+    if n_total is None:
+        n_total = float(D.allreduce_sum_(gt_d.sum().double()).item())              # train_data.N (utils/dataloader.py:159)
+    ch = net.reconstructor.in_channels
+    if emb is None:
+        emb = torch.ones((n_leaf_all, ch, 2, 2, 2), dtype=torch.float32)            # NVFPCC.py:120-122
+    emb_local = emb[lo:hi].detach().to(dev, torch.float32).clone().requires_grad_(True)
+    opt = FusedAdam(net.parameters(), lr=lr)
+    opt_emb = torch.optim.Adam([emb_local], lr=lr * wemb)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, list(milestones), 0.1)
+    sch_emb = torch.optim.lr_scheduler.MultiStepLR(opt, list(milestones), 0.1)      # sic: wraps opt (NVFPCC.py:126)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        for _ in range(start_epoch):
+            sch_emb.step()
+            sch.step()
+    if batchsize % ws != 0:
+        raise ValueError("batchsize must be a multiple of the number of ranks")
+    B = batchsize // ws
+    wstep = WeightStep(net, opt, B, n_total, lmbda, w1, w2, focal_alpha, use_graph=use_graph, device=dev)
+    estep = EmbeddingStep(net, emb_local, opt_emb, n_total, lmbda, w1, w2, focal_alpha)
+    steps = (n_leaf + B - 1) // B
+    if ws > 1:                                                                      # same step count on every rank
+        steps = (D.block_range(n_leaf_all, 0, ws)[1] + B - 1) // B                  # rank 0 holds the longest range
+    order = torch.tensor([dataset_index(i, n_leaf, dataset_shuffle) for i in range(n_leaf)], device=dev)
+    history = []
+    acc = torch.zeros(len(STAT_NAMES), device=dev)
+    q = 1 if start_epoch < phase_change else 2
+    for epoch in range(start_epoch, epochs):
+        if epoch == phase_change:
+            q = 2
+        acc.zero_()
+        for s in range(steps):
+            idx = order[(torch.arange(B, device=dev) + s * B) % n_leaf]
+            st = wstep.step(emb_local.detach()[idx], gt_d[idx], dist_d[idx], q=q)
+            acc += st
+        est = estep.step(gt_d, dist_d, q)
+        with warnings.catch_warnings():          # the graph replays opt.step(); the schedulers cannot see it
+            warnings.simplefilter("ignore", UserWarning)
+            sch_emb.step()
+            sch.step()
+        rec = dict(zip(STAT_NAMES, (acc / steps).tolist()))                         # the epoch's only host read
+        rec.update(epoch=epoch, q=q, emb_loss=float(est[0]), lr=float(opt.param_groups[0]["lr"]))
+        history.append(rec)
+        if log is not None:
+            log(rec)
+        if checkpoint_dir is not None and epoch % save_every == 0:
+            full = _gather_emb(emb_local, n_leaf_all, lo, hi, ws)
+            if rank == 0:
+                os.makedirs(checkpoint_dir, exist_ok=True)
+                torch.save(net.state_dict(), os.path.join(checkpoint_dir, '%04d.ckpt' % epoch))
+                torch.save(full, os.path.join(checkpoint_dir, '%04d_emb.ckpt' % epoch))
+    return _gather_emb(emb_local, n_leaf_all, lo, hi, ws), history
+
+
+def _gather_emb(emb_local: torch.Tensor, n_all: int, lo: int, hi: int, ws: int) -> torch.Tensor:
+    """All embedding rows on every rank (N x ch x 8 floats: the only time embeddings cross ranks)."""
+    e = emb_local.detach()
+    if ws == 1:
+        return e.clone().requires_grad_(True)
+    full = torch.zeros((n_all,) + tuple(e.shape[1:]), dtype=e.dtype, device=e.device)
+    full[lo:hi] = e
+    D.allreduce_sum_(full)
+    return full.requires_grad_(True)
