@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--decode-steps", type=int, default=5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly (no CUDA graph)")
     ap.add_argument("--skip-epoch", action="store_true", help="skip the embedding-loop / epoch measurement")
+    ap.add_argument("--skip-prep", action="store_true", help="skip the grid-builder and encode/decode-driver measurements")
     return ap.parse_args()
 
 
@@ -211,12 +212,13 @@ class TrainWorkload:
         self.args, self.rank, self.world = args, rank, world
         nb = min(args.train_blocks, origins.shape[0])
         sel = (np.arange(nb) + rank * nb) % origins.shape[0]
-        gt, dist_ = synth.gt_and_dist(pts, origins[sel])
+        from nvfpcc_b200 import grids
+        g = grids.build_grids(pts, origins[sel], want_gt=True, want_dist64=False, want_dist32=True)   # util_get_grids.py on the GPU
         self.n_total = float(pts.shape[0])
-        self.gt_host = torch.from_numpy(gt).float().pin_memory()
-        self.dist_host = torch.from_numpy(dist_).float().pin_memory()
-        self.gt_dev = self.gt_host.cuda()
-        self.dist_dev = self.dist_host.cuda()
+        self.gt_dev = g["gt"].float()
+        self.dist_dev = g["dist32"]
+        self.gt_host = self.gt_dev.cpu().pin_memory()
+        self.dist_host = self.dist_dev.cpu().pin_memory()
         self.nb = nb
         self.net = make_net(args.chanstr, "cuda")
         from nvfpcc_b200 import trainer
@@ -322,6 +324,128 @@ def embedding_loop(tw, args, world, n_blocks, flush):
     del es, opt_emb, emb, gt, dst
     torch.cuda.empty_cache()
     return ms
+
+
+# ----------------------------------------------------------------------------- rows either side of the path
+def hbm_peak_gbs():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the
+    profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6550.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
+
+
+def grids_bench(args, rank, world, pts, origins, flush, with_cpu):
+    """util_get_grids.py:19-46 for the rank's leaves: nvf_build_grids (cells + per-leaf exact distance
+    transform), inputs resident in HBM; e2e = host points/origins in, uint8 gt + float64 dist out to host."""
+    from nvfpcc_b200 import dist as D
+    from nvfpcc_b200 import grids
+    lo, hi = D.block_range(origins.shape[0], rank, world)
+    p_dev = torch.from_numpy(pts).cuda()
+    o_dev = torch.from_numpy(origins[lo:hi].astype(np.int32)).cuda()
+    # aligned octree leaves: the occupied 32^3 cells of the cloud ARE the leaves
+    kw = dict(want_gt=True, want_dist64=True, want_dist32=True, check=False, max_cells=int(origins.shape[0]))
+    for _ in range(2):
+        grids.build_grids(p_dev, o_dev, **kw)
+    reps = 5
+    ms = timed(lambda i: grids.build_grids(p_dev, o_dev, **kw), reps, world, pre=lambda: flush_l2(flush)) / reps
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    r = grids.build_grids(pts, origins[lo:hi], want_gt=True, want_dist64=True)
+    gt_h, dist_h = r["gt"].cpu(), r["dist"].cpu()
+    barrier_sync(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    n_all = origins.shape[0]
+    vox = n_all * 32768
+    bytes_per_vox = 1 + 8 + 4                                  # gt u8 + dist f64 + dist f32 written per grid voxel
+    alg_bytes = (hi - lo) * 32768 * bytes_per_vox + pts.shape[0] * 12 + (hi - lo) * 12
+    peak, src = hbm_peak_gbs()
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    out = dict(metric="grid_voxels_per_sec", value=vox / (ms * 1e-3), unit="voxels/s", ms_per_step=ms, blocks=int(n_all),
+               points=int(pts.shape[0]), gpu_launches=3 * reps, occupied=int(gt_h.sum()) if world == 1 else None,
+               workload="gt_grid + dist of all %d leaves of the synthetic cloud (util_get_grids.py), exact, float64" % n_all,
+               e2e=dict(value=vox / (e2e_ms * 1e-3), unit="voxels/s", h2d_bytes_per_step=int(pts.shape[0] * 12 + (hi - lo) * 12),
+                        d2h_bytes_per_step=int((hi - lo) * 32768 * 9)),
+               roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                             per_gpu=True, algorithmic_bytes_per_block=32768 * bytes_per_vox, peak_source=src,
+                             kernel="k_edt_blocks", note="integer shared-memory work per plane, not HBM, limits this "
+                                                         "kernel today (DESIGN.md section 3)"))
+    if with_cpu:
+        from oracle import grids_oracle as GO
+        nb = min(48, n_all)
+        t0 = time.perf_counter()
+        GO.build_grids(pts, origins[:nb], workers=-1)
+        el = time.perf_counter() - t0
+        out["cpu_baseline"] = dict(value=nb * 32768 / el, unit="voxels/s", cores=os.cpu_count(), kind="port",
+                                   sample="%d leaves (%.1f s) of the oracle port: scipy cKDTree queries on all host "
+                                          "threads (the reference itself calls open3d's KD-tree once per voxel from "
+                                          "Python, util_get_grids.py:37-39)" % (nb, el))
+    return out
+
+
+def codec_bench(args, rank, world, origins, with_cpu):
+    """encode() / decode() of the reference (NVFPCC.py:395-652) through nvfpcc_b200.codec: wall time from the
+    embeddings / the pack in HOST memory to the reconstructed cloud in host memory, entropy coding included."""
+    from nvfpcc_b200 import codec, entropy, network, synth
+    net = make_net(args.chanstr, "cpu")
+    sd = net.state_dict()
+    sd.update(synth.random_kernel_deltas(sd, seed=1, sigma=0.05, quantize=True))
+    net.load_state_dict(sd)
+    net = net.cuda()
+    n = origins.shape[0]
+    emb = torch.from_numpy(synth.random_latents(n, 3, seed=3)) * 0.7
+    with torch.no_grad():
+        lat = net.get_latent_code(emb[:64].cuda())["quantized_latent"]
+    calibrate_threshold_bias(net, lat, 0.64)
+    state = codec.quantize_state({k: v.detach().cpu() for k, v in net.state_dict().items()}, 16)
+    net.load_state_dict(state, strict=False)
+    codec.encode(net, emb[:64], origins[:64], 0.64, weights_state=state)       # warm-up
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    enc = codec.encode(net, emb, origins, 0.64, weights_state=state)
+    barrier_sync(world)
+    enc_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    network.set_seed(synth.synthetic_seed())
+    t0 = time.perf_counter()
+    dec = codec.decode(enc["total_pack"], 3, args.chanstr, 0.64)
+    barrier_sync(world)
+    dec_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    if rank != 0:
+        return None
+    lp = enc["total_pack"]["latent_pack"]
+    out = dict(metric="decoded_voxels_per_sec", workload="encode() -> pack -> decode() of all %d leaves, 1/16-quantised "
+               "weights, thh 0.64, host to host (BASELINE.json configs[2])" % n,
+               encode_ms=enc_ms, decode_ms=dec_ms, value=n * 32768 / (dec_ms * 1e-3), unit="voxels/s",
+               points=int(dec.shape[0]), rc_enc_equals_rc_dec=bool(np.array_equal(dec, enc["points"])),
+               latent_stream_bytes=len(lp["latent_byte_stream"]),
+               weight_stream_bytes=len(enc["total_pack"]["net_weight_pack"]["bit_stream"]),
+               bpp=(enc["latent_bits"] + enc["net_bits"]) / max(1, dec.shape[0]))
+    # entropy coder alone: in-process coder vs the reference's helper binary (when compiled into oracle/_ref)
+    s = tuple(lp["shape"])
+    mu = (np.broadcast_to(lp["mu"].numpy().astype(np.float32), s).reshape(-1) + np.float32(512)).astype(np.float32)
+    sg = np.broadcast_to(lp["sigma"].numpy().astype(np.float32), s).reshape(-1).astype(np.float32)
+    sym = (entropy.decode_latents(lp).reshape(-1) + 512).astype(np.int16)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        stream = entropy.arithmetic_encode(sym, mu, sg)
+        entropy.arithmetic_decode(stream, mu, sg)
+    el = (time.perf_counter() - t0) / 5
+    out["entropy"] = dict(symbols=int(sym.size), value=sym.size / el, unit="symbols/s (encode + decode)")
+    exe = os.path.join(ROOT, "oracle", "_ref", "module_arithmeticcoding")
+    if with_cpu and os.path.isfile(exe):
+        length = np.array([sym.size], dtype=np.int64)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, "e", "1", "1"], input=length.tobytes() + sym.tobytes() + mu.tobytes() + sg.tobytes(),
+                           stdout=subprocess.PIPE).stdout
+        subprocess.run([exe, "d", "1", "1"], input=length.tobytes() + mu.tobytes() + sg.tobytes() + r, stdout=subprocess.PIPE)
+        el_ref = time.perf_counter() - t0
+        out["entropy"]["cpu_baseline"] = dict(value=sym.size / el_ref, unit="symbols/s (encode + decode)", cores=1,
+                                              kind="reference", same_stream=bool(r == stream),
+                                              sample="the reference's module_arithmeticcoding helper (oracle/_ref), "
+                                                     "all %d latent symbols, subprocess as in NVFPCC.py:461-470" % sym.size)
+    return out
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -494,6 +618,13 @@ def main():
     de2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.decode_steps
     dec_e2e = dw.n_all * 32768 / (de2e_ms * 1e-3)
 
+    # ---------------- rows either side of the path: grid builder, encode/decode drivers ----------------
+    prep = None
+    if not args.skip_prep:
+        with_cpu = (not args.skip_cpu_baseline) and world == 1
+        prep = dict(grids=grids_bench(args, rank, world, pts, origins, flush, with_cpu),
+                    codec=codec_bench(args, rank, world, origins, with_cpu))
+
     if rank != 0:
         return
     peaks = ffma_peak(binding)
@@ -526,6 +657,8 @@ def main():
                                   timing="CUDA events around the nvf_decode launch sequence (pack + fused kernel + scan + emit)",
                                   kernel="k_decode_fused_A" if cs == "8,16,8,8" else "layer-wise kernels")),
     )
+    if prep is not None:
+        line["grids"], line["codec"] = prep["grids"], prep["codec"]
     if epoch is not None:
         epoch["embedding_loop_frac_of_peak"] = epoch["embedding_loop_tflops"] / peak
         line["epoch"] = epoch

@@ -64,7 +64,8 @@ def build_grids(points, origins, *, max_cells: Optional[int] = None, max_radius:
 
     points  (P,3) integer voxel coordinates (numpy or torch); origins (N,3) leaf origins.
     Returns CUDA tensors: 'gt' uint8 / 'dist' float64 / 'dist32' float32, each [N,1,32,32,32],
-    'd2' uint16 [N,32768], and 'status' (int32 [1]).  With check=True (one host sync) a
+    'd2' uint16 [N,32768], and 'status' (int32 [1]).  max_cells=None counts the cloud's occupied 32^3 cells
+    first (one small sort + host sync); pass it to stay asynchronous.  With check=True (one host sync) a
     non-zero status raises: leaves without any point, or more occupied cells than max_cells.
     """
     if not torch.cuda.is_available():
@@ -87,8 +88,9 @@ def build_grids(points, origins, *, max_cells: Optional[int] = None, max_radius:
     pts = as_i32(points, "points")
     org = as_i32(origins, "origins")
     n, npts = int(org.shape[0]), int(pts.shape[0])
-    if max_cells is None:
-        max_cells = max(8 * n, 64)
+    if max_cells is None:                    # distinct (point >> 5) cells of the cloud, counted on the device
+        c = (pts.to(torch.int64) >> 5) + (1 << 20)
+        max_cells = max(int(torch.unique((c[:, 0] << 42) | (c[:, 1] << 21) | c[:, 2]).numel()), 64) if npts else 64
     nbytes = workspace_bytes(max_cells)
     ws = b.cached_workspace(nbytes, dev, "grids")
     out: Dict[str, torch.Tensor] = {}

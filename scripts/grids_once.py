@@ -12,12 +12,12 @@ pts = synth.sphere_shell_points(a.resolution)
 origins = synth.leaf_origins(pts)
 p = torch.from_numpy(pts).cuda(); o = torch.from_numpy(origins).cuda()
 for _ in range(2):
-    r = grids.build_grids(p, o, want_dist32=True)
+    r = grids.build_grids(p, o, want_dist32=True, max_cells=origins.shape[0])
 torch.cuda.synchronize()
 ts = []
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); r = grids.build_grids(p, o, want_dist32=True, check=False); e1.record(); torch.cuda.synchronize()
+    e0.record(); r = grids.build_grids(p, o, want_dist32=True, check=False, max_cells=origins.shape[0]); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 n = origins.shape[0]
 ms = float(np.median(ts))
