@@ -327,6 +327,17 @@ def embedding_loop(tw, args, world, n_blocks, flush):
 
 
 # ----------------------------------------------------------------------------- rows either side of the path
+def measured_traffic(kind, **match):
+    """roofline.traffic: DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), only
+    when this run's workload is the captured one; otherwise None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            e = json.load(f)[kind]
+        return e["dram_bytes"] if all(e.get(k) == v for k, v in match.items()) else None
+    except Exception:
+        return None
+
+
 def hbm_peak_gbs():
     """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the
     profiling guide's fallback."""
@@ -368,7 +379,8 @@ def grids_bench(args, rank, world, pts, origins, flush, with_cpu):
                workload="gt_grid + dist of all %d leaves of the synthetic cloud (util_get_grids.py), exact, float64" % n_all,
                e2e=dict(value=vox / (e2e_ms * 1e-3), unit="voxels/s", h2d_bytes_per_step=int(pts.shape[0] * 12 + (hi - lo) * 12),
                         d2h_bytes_per_step=int((hi - lo) * 32768 * 9)),
-               roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+               roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                             traffic=measured_traffic("grids", blocks=int(hi - lo)),
                              per_gpu=True, algorithmic_bytes_per_block=32768 * bytes_per_vox, peak_source=src,
                              kernel="k_edt_blocks", note="integer shared-memory work per plane, not HBM, limits this "
                                                          "kernel today (DESIGN.md section 3)"))
@@ -639,7 +651,9 @@ def main():
         e2e=dict(value=train_e2e, unit="blocks/s", h2d_bytes_per_step=TrainWorkload.h2d_bytes,
                  d2h_bytes_per_step=TrainWorkload.d2h_bytes),
         gpu_launches=int(launches),
-        roofline=dict(bound="fp32", achieved=t_ach, peak=peak, unit="TFLOP/s", frac=t_ach / peak, traffic=None,
+        roofline=dict(bound="fp32", achieved=t_ach, peak=peak, unit="TFLOP/s", frac=t_ach / peak,
+                      traffic=measured_traffic("train", chanstr=cs, blocks_per_step=HP["batch"]),
+                      hbm_gbs=(measured_traffic("train", chanstr=cs, blocks_per_step=HP["batch"]) or 0) / (ms_step * 1e-3) / 1e9,
                       per_gpu=True, algorithmic_flop_per_block=F_TRAIN[cs],
                       peak_source="live nvf_ffma_microbench (MEASURED_PEAKS.json has no fp32 figure): "
                                   "ffma %.1f, ffma2 %.1f TFLOP/s; theoretical 74.4 at 1965 MHz; denominator = min"
@@ -653,7 +667,9 @@ def main():
                     e2e=dict(value=dec_e2e, unit="voxels/s",
                              h2d_bytes_per_step=int(dw.n_all * (96 + 12)), d2h_bytes_per_step=int(dw.points * 12)),
                     roofline=dict(bound="fp32", achieved=d_ach, peak=peak, unit="TFLOP/s", frac=d_ach / peak,
-                                  traffic=None, per_gpu=True, algorithmic_flop_per_block=F_DEC[cs],
+                                  traffic=measured_traffic("decode", chanstr=cs, blocks=int(dw.n_local)),
+                                  hbm_gbs=(measured_traffic("decode", chanstr=cs, blocks=int(dw.n_local)) or 0) / (dkernel_ms * 1e-3) / 1e9,
+                                  per_gpu=True, algorithmic_flop_per_block=F_DEC[cs],
                                   timing="CUDA events around the nvf_decode launch sequence (pack + fused kernel + scan + emit)",
                                   kernel="k_decode_fused_A" if cs == "8,16,8,8" else "layer-wise kernels")),
     )
