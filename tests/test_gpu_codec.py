@@ -116,3 +116,13 @@ def test_pack_is_plain_pickle_and_errors(gpu, tmp_path):
     bad["reconstructor.conv2.kernel"] = state["reconstructor.conv2.kernel"] + 0.013
     with pytest.raises(ValueError):
         codec.encode(net, emb, origins, THH, weights_state=bad)
+
+
+def test_zero_leaves_round_trip(gpu):
+    from nvfpcc_b200 import codec, network, synth
+    net, emb, origins, state = make_case(n_blocks=8)
+    enc = codec.encode(net, emb[:0], origins[:0], THH, weights_state=state)
+    assert enc["points"].shape == (0, 3) and enc["total_pack"]["origins"].shape == (0, 3)
+    network.set_seed(synth.synthetic_seed())
+    dec = codec.decode(enc["total_pack"], 3, "8,16,8,8", THH)
+    assert dec.shape == (0, 3)

@@ -108,3 +108,42 @@ def test_cli_writes_the_reference_files(tmp_path, monkeypatch):
     assert gt.dtype == np.uint8 and dist.dtype == np.float64 and org.dtype == np.float64
     gt_ref, dist_ref = GO.build_grids(pts, origins)
     assert np.array_equal(gt, gt_ref) and np.array_equal(dist, dist_ref) and np.array_equal(org, origins)
+
+
+def test_full_vox10_cloud_properties_and_sampled_oracle():
+    """BASELINE size (849 338 points, 1247 leaves): size-independent properties of a distance field on every leaf,
+    exact comparison with the oracle on a random sample of leaves."""
+    from nvfpcc_b200 import grids, synth
+    pts = synth.sphere_shell_points(1024)
+    origins = synth.leaf_origins(pts)
+    r = grids.build_grids(pts, origins, want_d2=True, max_cells=origins.shape[0])
+    gt, dist = r["gt"], r["dist"]
+    assert int(gt.sum().item()) == pts.shape[0]                        # every cloud point is one occupied voxel
+    assert bool(((dist == 0) == (gt == 1)).all())
+    assert float(dist.max().item()) <= 31 * np.sqrt(3) + 1e-9          # non-empty leaves bound the distance
+    d = dist[:, 0]
+    for ax in (1, 2, 3):                                               # 1-Lipschitz along every axis
+        assert float((d.narrow(ax, 1, 31) - d.narrow(ax, 0, 31)).abs().max().item()) <= 1.0 + 1e-12
+    d2 = r["d2"].cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sqrt(d2.astype(np.float64)).reshape(dist.shape), dist.cpu().numpy())
+    # the occupied voxels, mapped back through the origins, are exactly the cloud
+    idx = torch.nonzero(gt[:, 0]).cpu().numpy()
+    back = origins[idx[:, 0]].astype(np.int64) + idx[:, 1:]
+    key = lambda a: np.sort(a[:, 0] * (1 << 40) + a[:, 1] * (1 << 20) + a[:, 2])
+    assert np.array_equal(key(back), key(pts.astype(np.int64)))
+    sel = np.random.default_rng(0).choice(origins.shape[0], size=24, replace=False)
+    gt_ref, dist_ref = GO.build_grids(pts, origins[sel], workers=-1)
+    assert np.array_equal(dist.cpu().numpy()[sel], dist_ref) and np.array_equal(gt.cpu().numpy()[sel], gt_ref)
+
+
+def test_empty_inputs():
+    from nvfpcc_b200 import _lib, grids
+    pts = np.array([[1, 2, 3]], dtype=np.int32)
+    r = grids.build_grids(pts, np.zeros((0, 3), np.int32))
+    assert r["gt"].shape == (0, 1, 32, 32, 32) and r["dist"].shape == (0, 1, 32, 32, 32)
+    r = grids.build_grids(np.zeros((0, 3), np.int32), np.zeros((1, 3), np.int32), check=False)
+    assert int(r["status"].item()) == grids.STATUS_NOT_FOUND
+    with pytest.raises(ValueError):
+        grids.build_grids(np.zeros((4, 2), np.int32), np.zeros((1, 3), np.int32))
+    with pytest.raises(ValueError):
+        grids.build_grids(np.array([[0.5, 1, 2]]), np.zeros((1, 3), np.int32))
