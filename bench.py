@@ -532,6 +532,31 @@ def run_reference(args):
     pts, origins = make_cloud(args.resolution)
     cb, sec_per = cpu_train_baseline(args, pts, origins, max_steps=args.steps, warmup=args.warmup)
     dec = cpu_decode_baseline(args, origins)
+    # rows either side of the path, CPU side: the grid oracle (scipy cKDTree, all threads) and the reference's own
+    # arithmetic-coding helper (oracle/_ref) on seeded latents of the cloud's size
+    from oracle import grids_oracle as GO
+    nb = min(48, origins.shape[0])
+    t0 = time.perf_counter()
+    GO.build_grids(pts, origins[:nb], workers=-1)
+    el = time.perf_counter() - t0
+    grids_ref = dict(metric="grid_voxels_per_sec", value=nb * 32768 / el, unit="voxels/s",
+                     cpu_baseline=dict(value=nb * 32768 / el, unit="voxels/s", cores=os.cpu_count(), kind="port",
+                                       sample="%d leaves (%.1f s), scipy cKDTree restatement of util_get_grids.py" % (nb, el)))
+    entropy_ref = None
+    exe = os.path.join(ROOT, "oracle", "_ref", "module_arithmeticcoding")
+    if os.path.isfile(exe):
+        rng = np.random.default_rng(0)
+        n = origins.shape[0] * 24
+        sym = (np.clip(np.rint(rng.normal(0, 3, n)), -512, 511) + 512).astype(np.int16)
+        mu, sg = np.full(n, 512, np.float32), np.full(n, 3, np.float32)
+        length = np.array([n], dtype=np.int64)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, "e", "1", "1"], input=length.tobytes() + sym.tobytes() + mu.tobytes() + sg.tobytes(),
+                           stdout=subprocess.PIPE).stdout
+        subprocess.run([exe, "d", "1", "1"], input=length.tobytes() + mu.tobytes() + sg.tobytes() + r, stdout=subprocess.PIPE)
+        el = time.perf_counter() - t0
+        entropy_ref = dict(value=n / el, unit="symbols/s (encode + decode)", cores=1, kind="reference", symbols=int(n),
+                           sample="module_arithmeticcoding compiled from the reference source, subprocess as in NVFPCC.py:461-470")
     line = dict(impl="reference", metric="train_blocks_per_sec", value=cb["value"], unit="blocks/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec_per * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -539,7 +564,8 @@ def run_reference(args):
                 e2e=dict(value=cb["value"], unit="blocks/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 decode=dict(metric="decoded_voxels_per_sec", value=dec["value"], unit="voxels/s", cpu_baseline=dec,
                             e2e=dict(value=dec["value"], unit="voxels/s", h2d_bytes_per_step=0,
-                                     d2h_bytes_per_step=0)))
+                                     d2h_bytes_per_step=0)),
+                grids=grids_ref, codec=dict(entropy=entropy_ref))
     print(json.dumps(line))
 
 
@@ -654,6 +680,9 @@ def main():
         roofline=dict(bound="fp32", achieved=t_ach, peak=peak, unit="TFLOP/s", frac=t_ach / peak,
                       traffic=measured_traffic("train", chanstr=cs, blocks_per_step=HP["batch"]),
                       hbm_gbs=(measured_traffic("train", chanstr=cs, blocks_per_step=HP["batch"]) or 0) / (ms_step * 1e-3) / 1e9,
+                      hbm=dict(algorithmic_bytes_per_block=164032, achieved_gbs=train_value / world * 164032 / 1e9,
+                               peak_gbs=hbm_peak_gbs()[0], note="96 B emb + 32 KB gt + 128 KB dist + 96 B d_emb per block: "
+                               "the path is FP32-FMA bound, HBM is <0.1 % utilised by algorithmic bytes"),
                       per_gpu=True, algorithmic_flop_per_block=F_TRAIN[cs],
                       peak_source="live nvf_ffma_microbench (MEASURED_PEAKS.json has no fp32 figure): "
                                   "ffma %.1f, ffma2 %.1f TFLOP/s; theoretical 74.4 at 1965 MHz; denominator = min"
