@@ -238,7 +238,7 @@ class TrainWorkload:
         """One weight-loop step (NVFPCC.py:149-223): batch -> static buffers -> fused fwd + loss + bwd +
         all-reduce + Adam (one CUDA-graph replay), inputs resident in HBM."""
         idx = self.idx_dev[i % len(self.idx_dev)]
-        st = self.ws.step(self.emb[idx], self.gt_dev[idx], self.dist_dev[idx], q=1)
+        st = self.ws.step_indexed(self.emb, self.gt_dev, self.dist_dev, idx, q=1)
         self.last_loss = st[0]
         return st
 

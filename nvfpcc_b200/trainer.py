@@ -188,10 +188,22 @@ class WeightStep:
                     if torch.is_tensor(v):
                         v.zero_()
 
+    def step_indexed(self, emb_all: torch.Tensor, gt_all: torch.Tensor, dist_all: torch.Tensor, idx: torch.Tensor,
+                     q: int = 1) -> torch.Tensor:
+        """step() for device-resident datasets (float32): rows `idx` are gathered straight into the static
+        buffers (three index_select launches, no temporaries, no copies)."""
+        torch.index_select(emb_all.detach(), 0, idx, out=self.emb)
+        torch.index_select(gt_all, 0, idx, out=self.gt)
+        torch.index_select(dist_all, 0, idx, out=self.dist)
+        return self._run(q)
+
     def step(self, emb_batch: torch.Tensor, gt: torch.Tensor, dist_: torch.Tensor, q: int = 1) -> torch.Tensor:
         self.emb.copy_(emb_batch.detach(), non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
         self.dist.copy_(dist_, non_blocking=True)
+        return self._run(q)
+
+    def _run(self, q: int) -> torch.Tensor:
         if not self.use_graph:
             self._body(q)
             return self.stats
@@ -374,7 +386,7 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
         acc.zero_()
         for s in range(steps):
             idx = order[(torch.arange(B, device=dev) + s * B) % n_leaf]
-            st = wstep.step(emb_local.detach()[idx], gt_d[idx], dist_d[idx], q=q)
+            st = wstep.step_indexed(emb_local, gt_d, dist_d, idx, q=q)
             acc += st
         est = estep.step(gt_d, dist_d, q)
         with warnings.catch_warnings():          # the graph replays opt.step(); the schedulers cannot see it
