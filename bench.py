@@ -525,6 +525,63 @@ def cpu_decode_baseline(args, origins, budget_s=12.0):
                 sample="%d blocks at batch 1 (%.1f s) of the oracle port, torch CPU fp32" % (n, el))
 
 
+def torch_cuda_baseline(args, pts, origins, budget_s=6.0):
+    """The reference's op sequence (oracle port = plain torch ops -> cuDNN / ATen kernels) on THIS B200 with TF32
+    off: the 'same box, stock framework' bar of SURVEY.md 8d.  Not the product path - a reported baseline.
+    train: weight-loop steps at batch 16 with the per-step `.item()` read of train() (NVFPCC.py:190-221);
+    decode: the batch-1 loop of decode() (NVFPCC.py:625-638) incl. the per-block device->host reads."""
+    from nvfpcc_b200 import synth
+    from oracle import nvf_oracle as O
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        dev = torch.device("cuda")
+        sd = {k: v.clone().to(dev) for k, v in oracle_state(args.chanstr).items() if not k.startswith("_")}
+        params = {k: v.requires_grad_(True) for k, v in sd.items() if not k.endswith(("_init", "pedestal"))}
+        opt = torch.optim.Adam(list(params.values()), lr=HP["lr"])
+        B = HP["batch"]
+        gt, dist_ = synth.gt_and_dist(pts, origins[:B])
+        gt, dist_ = torch.from_numpy(gt).float().to(dev), torch.from_numpy(dist_).float().to(dev)
+        emb = torch.ones(B, 3, 2, 2, 2, device=dev, requires_grad=True)
+        n_total = float(pts.shape[0])
+
+        def one():
+            opt.zero_grad()
+            res = O.net_forward(emb, sd, "train", 1)
+            L = O.train_loss(res, gt, dist_, gt.sum(), n_total, HP["lmbda"], HP["w1"], HP["w2"])
+            L["loss"].backward()
+            opt.step()
+            return float(L["loss"].item())
+
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget_s and n < 200:
+            one()
+            n += 1
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        train = dict(value=n * B / el, unit="blocks/s", sample="%d weight-loop steps at batch %d (%.1f s)" % (n, B, el))
+        lat = torch.from_numpy(synth.random_latents(256, 3, seed=0)).to(dev)
+        sd_d = {k: v.detach() for k, v in sd.items()}
+        with torch.no_grad():
+            O.reconstruct(lat[:1], sd_d, 2)
+            torch.cuda.synchronize()
+            t0, m = time.perf_counter(), 0
+            while m < 256 and time.perf_counter() - t0 < budget_s:
+                pr = O.reconstruct(lat[m:m + 1], sd_d, 2)
+                O.threshold_points(pr.cpu(), origins[m:m + 1], HP["thh"])
+                m += 1
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+        dec = dict(value=m * 32768 / el, unit="voxels/s", sample="%d blocks at batch 1 (%.1f s)" % (m, el))
+        return dict(kind="port on torch-CUDA (cuDNN/ATen, TF32 off) on the same B200", train=train, decode=dec)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -708,6 +765,7 @@ def main():
         epoch["embedding_loop_frac_of_peak"] = epoch["embedding_loop_tflops"] / peak
         line["epoch"] = epoch
     if not args.skip_cpu_baseline and world == 1:
+        line["torch_cuda_baseline"] = torch_cuda_baseline(args, pts, origins)
         line["cpu_baseline"], _ = cpu_train_baseline(args, pts, origins, budget_s=15.0)
         line["decode"]["cpu_baseline"] = cpu_decode_baseline(args, origins, budget_s=10.0)
     print(json.dumps(line))

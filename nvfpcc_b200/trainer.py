@@ -38,6 +38,12 @@ def _loss_terms(net, emb, gt, dst, q, n_total, lmbda, w1, w2, focal_alpha, n_pts
     return loss, stats, sums
 
 
+def forward_loss(net, emb, gt, dist_, q, n_total, lmbda, w1, w2, focal_alpha=0.9, n_pts=None):
+    """SURVEY.md 8b `forward_loss`: Net.forward + the rate-distortion loss of train() in one call ->
+    (loss, stats[7] on the device (STAT_NAMES), sums[20]); differentiable w.r.t. emb and the network."""
+    return _loss_terms(net, emb, gt, dist_, q, n_total, lmbda, w1, w2, focal_alpha, n_pts=n_pts)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam (defaults of train(), NVFPCC.py:116,124: betas (0.9, 0.999), eps 1e-8, no weight decay,
     no amsgrad) over ONE flat buffer: all parameters are re-pointed to views of `flat`, the moments are flat too,
