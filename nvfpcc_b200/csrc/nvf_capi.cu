@@ -40,9 +40,11 @@ SidePool g_side[kMaxDevices];
 // Optional programmatic stream serialisation (PDL), NVF_PDL=1: a kernel's CTAs may be scheduled while the
 // previous kernel of the stream is still draining; they block in griddepcontrol.wait (pdl_entry(), first
 // statement of every kernel) until that kernel has completed and flushed, so semantics are those of an
-// ordinary in-order stream.  Measured on B200 (round 1, graph-captured 16-block train step): 0.98 ms with PDL
-// vs 0.90 ms without - the early-resident waiting CTAs take the slots the side-stream weight-gradient kernels
-// would otherwise fill - so the default is OFF (plain launches; pdl_entry() is then a no-op).
+// ordinary in-order stream.  Measured on B200 (round 1, graph-captured 16-block train step): with every kernel
+// releasing its dependents at entry 0.98 ms vs 0.90 ms without PDL - the early-resident waiting CTAs take the
+// slots the side-stream weight-gradient kernels would otherwise fill; with the heavy kernels releasing them only
+// after their main loop (pdl_entry_heavy / pdl_trigger) 0.899 ms vs 0.891 ms - neutral, the captured graph already
+// hides launch latency - so the default stays OFF (plain launches; the PDL instructions are then no-ops).
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -467,6 +469,9 @@ struct DevLauncher {
     int grid = (n_sms * MINB + G::GROUPS - 1) / G::GROUPS;
     if (grid > items) grid = items;
     if (grid * G::GROUPS > kMaxPartialCtas) grid = kMaxPartialCtas / G::GROUPS;
+    // persistent CTAs: the same number on every SM (304 CTAs on 148 SMs would leave eight SMs with three CTAs
+    // while the others hold two, and the kernel ends with those eight)
+    if (grid * G::GROUPS > n_sms) grid = (grid * G::GROUPS / n_sms) * n_sms / G::GROUPS;
     float* partial = take_partial((size_t)grid * G::GROUPS * G::OUT_FLOATS);
     if (!partial) return false;
     if (!chansum_fast(c)) return false;

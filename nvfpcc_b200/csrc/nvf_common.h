@@ -120,16 +120,23 @@ NVF_HD void p2_load_w8(const float* wp, p2 (&w)[4]) {
   p2_ld2(wp + 4, w[2], w[3]);
 }
 
-// Programmatic dependent launch: first statement of every kernel.  Lets the NEXT kernel of the stream start
-// being scheduled as soon as all CTAs of this one are resident, then waits until the PREVIOUS kernel has
-// completed and its writes are visible (no-ops when the kernel was launched without the PDL attribute).
+// Programmatic dependent launch (only in effect when the launch carries the PDL attribute, NVF_PDL=1).
+//   pdl_entry()       first statement of every kernel: wait until the PREVIOUS kernel of the stream has completed and
+//                     its writes are visible.  Small kernels also release their dependents right away.
+//   pdl_entry_heavy() the long-running kernels wait only; they call pdl_trigger() after their main loop, so the
+//                     next kernel's CTAs are scheduled into the SMs this kernel's tail frees up instead of sitting
+//                     resident (and holding registers / shared memory) for its whole duration.
 #if defined(__CUDA_ARCH__)
 NVF_D void pdl_entry() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+NVF_D void pdl_entry_heavy() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+NVF_D void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #else
 inline void pdl_entry() {}
+inline void pdl_entry_heavy() {}
+inline void pdl_trigger() {}
 #endif
 
 NVF_HD float relu(float v) { return v > 0.f ? v : 0.f; }

@@ -49,7 +49,7 @@ struct ConvTFwdCfg {
 
 template <int CI, int CO, int DIN, int MINB, int KS = 1>
 __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN, KS>::THREADS, MINB) k_convT5_fwd(ConvTFwdParams p) {
-  pdl_entry();
+  pdl_entry_heavy();
   using G = ConvTFwdCfg<CI, CO, DIN, KS>;
   extern __shared__ __align__(128) float smem[];
   float* s_in = smem;
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN, KS>::THREADS, MINB) k
       }
     }
   }
+  pdl_trigger();
   float acc[2][4][8];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -248,7 +249,7 @@ struct ConvTDgradCfg {
 
 template <int CG, int CX, int DIN, int TY, int CGC, int MINB>
 __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, MINB) k_convT5_dgrad(ConvTDgradParams p) {
-  pdl_entry();
+  pdl_entry_heavy();
   using G = ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
   extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x;
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
     tma::cp_async_wait_all();
     __syncthreads();   // next chunk has landed; everyone is done with this one
   }
+  pdl_trigger();
   float acc[2][8][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -421,7 +423,7 @@ struct ConvTWgradCfg {
 
 template <int CI, int CO, int DIN, int TYB, int CIB, int MINB>
 __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) {
-  pdl_entry();
+  pdl_entry_heavy();
   using G = ConvTWgradCfg<CI, CO, DIN, TYB, CIB>;
   extern __shared__ __align__(128) float smem[];
   float* s_g = smem;
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(224, MINB) k_convT5_wgrad(ConvTWgradParams p) 
       }
     }
   }
+  pdl_trigger();
   if (!active) return;
   // partial in the layout [ci_local][co_local][kz][ky][kx]
   float* out = p.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * G::OUT_FLOATS;

@@ -196,12 +196,9 @@ class WeightStep:
 
     def step_indexed(self, emb_all: torch.Tensor, gt_all: torch.Tensor, dist_all: torch.Tensor, idx: torch.Tensor,
                      q: int = 1) -> torch.Tensor:
-        """step() for device-resident datasets (float32): rows `idx` are gathered straight into the static
-        buffers (three index_select launches, no temporaries, no copies)."""
-        torch.index_select(emb_all.detach(), 0, idx, out=self.emb)
-        torch.index_select(gt_all, 0, idx, out=self.gt)
-        torch.index_select(dist_all, 0, idx, out=self.dist)
-        return self._run(q)
+        """step() for device-resident datasets: rows `idx` of the three tensors.  (Advanced indexing + copy_:
+        measured 20 us for the six launches; torch.index_select(out=) picks a 42 us small-index kernel.)"""
+        return self.step(emb_all.detach()[idx], gt_all[idx], dist_all[idx], q)
 
     def step(self, emb_batch: torch.Tensor, gt: torch.Tensor, dist_: torch.Tensor, q: int = 1) -> torch.Tensor:
         self.emb.copy_(emb_batch.detach(), non_blocking=True)
