@@ -14,7 +14,8 @@
 //      transform plane by plane: per plane a0', every non-empty row a1' gives
 //      g(a1',k) = distance along a2 to the nearest set bit (CLZ/FFS on a 64-bit
 //      window), h(j,k) = min_a1' g^2 + (j-a1')^2, and the block's 32^3 squared
-//      distances (u16 in shared memory) take min(d2, h + (i-a0')^2).
+//      distances (16-bit halves in shared memory) take min(d2, h + (i-a0')^2); both
+//      min-plus loops run two values per instruction on VIADDMNMX.S16x2 (DPX).
 //      A leaf holds at least one point, so every distance is <= 31*sqrt(3) < 54:
 //      the own 32 planes are swept first, then only the outer planes within
 //      floor(sqrt(max d2)) of the block.  Everything is integer arithmetic;
@@ -121,10 +122,21 @@ struct EdtParams {
   CellTable T;
 };
 
+// Squared distances live in shared memory as signed 16-bit halves of 32-bit words so that the two inner loops
+// run on the packed DPX instruction VIADDMNMX.S16x2 (min(a + b, c) on both halves at once):
+//   - all real values are <= 3 * 84^2 < 0x3FFF = D2P_INF, and D2P_INF + 84^2 < 2^15, so no sum overflows;
+//   - d2p[(j * 32 + k) * D2P_PITCH + (i >> 1)] holds slices i (low half, i even) and i + 1 of column (j, k):
+//     a thread's 32 slices are 16 consecutive words (4 x LDS.128); the pitch of 20 words makes the 128-bit
+//     accesses of the 32 lanes (consecutive k) bank-conflict free.
+constexpr int D2P_PITCH = 20;
+constexpr uint32_t D2P_INF = 0x3FFFu, D2P_INF2 = 0x3FFF3FFFu;
+constexpr int SQ_OFF = 85, SQ_N = 172;   // sq2[d + SQ_OFF] = pack(d^2, (d + 1)^2), d in [-85, 86]
+
 struct EdtSmem {
-  uint16_t d2[L * L * L];         // 64 KB running squared distances [i][j][k]
-  uint16_t g2[EXT][L];            // squared distance along a2 for the rows of the current plane
-  uint32_t rowbits[EXT][ROWW];    // bit window of every row of the current plane
+  uint32_t d2p[L * L * D2P_PITCH];  // 80 KB running squared distances, see above
+  uint16_t g2[EXT][L];              // squared distance along a2 for the rows of the current plane (D2P_INF = none)
+  uint32_t rowbits[EXT][ROWW];      // bit window of every row of the current plane
+  uint32_t sq2[SQ_N];
   int32_t cellid[NC][NC][NC];
   int32_t slab_any[NC];
   int32_t rowlist[EXT];
@@ -192,28 +204,39 @@ __device__ __forceinline__ void edt_plane(EdtSmem& S, const EdtParams& p, int o0
     uint32_t g = 64;
     if (below) g = (uint32_t)__clzll((long long)below);
     if (above) g = min(g, (uint32_t)(__ffsll((long long)above) - 1));
-    S.g2[r][k] = g >= 64 ? (uint16_t)D2_INF : (uint16_t)(g * g);
+    S.g2[r][k] = g >= 64 ? (uint16_t)D2P_INF : (uint16_t)(g * g);
   }
   __syncthreads();
-  // ---- (4) thread (k, 4 rows j): h = min over rows, then the slices i within rlim of the plane
+  // ---- (4) thread (k, rows j0..j0+3): h(j) = min over rows of g2 + (j - row)^2, two rows j per DPX instruction
   const int k = tid & 31, j0 = (tid >> 5) * 4;
-  uint32_t h[4] = {1u << 20, 1u << 20, 1u << 20, 1u << 20};
+  uint32_t h01 = D2P_INF2, h23 = D2P_INF2;
+  const uint32_t* sq = S.sq2 + SQ_OFF + j0 + RMAX;   // sq[-r] = pack((j0 - jrel)^2, (j0 + 1 - jrel)^2), jrel = r - RMAX
+#pragma unroll 2
   for (int n = 0; n < nrows; ++n) {
     const int r = S.rowlist[n];
     const uint32_t v = S.g2[r][k];
-    const int dj = j0 - (r - RMAX);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) h[t] = min(h[t], v + (uint32_t)((dj + t) * (dj + t)));
+    const uint32_t vv = v * 0x10001u;
+    h01 = __viaddmin_s16x2(vv, sq[-r], h01);
+    h23 = __viaddmin_s16x2(vv, sq[2 - r], h23);
   }
+  //      then d2(i) = min(d2(i), h + (i - prel)^2) for the slices within rlim of the plane, eight slices per LDS.128
   const int i_lo = max(0, prel - rlim), i_hi = min(L - 1, prel + rlim);
+  if (i_lo > i_hi) return;
+  const int q_lo = i_lo >> 3, q_hi = i_hi >> 3;
+  const uint32_t* dd = S.sq2 + SQ_OFF - prel;        // dd[2w] = pack((2w - prel)^2, (2w + 1 - prel)^2)
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    if (h[t] >= D2_INF) continue;
-    uint16_t* col = S.d2 + (j0 + t) * L + k;
-    for (int i = i_lo; i <= i_hi; ++i) {
-      const uint32_t cand = h[t] + (uint32_t)((i - prel) * (i - prel));
-      const uint32_t cur = col[i * L * L];
-      if (cand < cur) col[i * L * L] = (uint16_t)cand;
+    const uint32_t ht = ((t < 2 ? h01 : h23) >> (16 * (t & 1))) & 0xFFFFu;
+    if (ht >= D2P_INF) continue;
+    const uint32_t hh = ht * 0x10001u;
+    uint4* col = reinterpret_cast<uint4*>(S.d2p + ((j0 + t) * L + k) * D2P_PITCH);
+    for (int q = q_lo; q <= q_hi; ++q) {
+      uint4 c = col[q];
+      c.x = __viaddmin_s16x2(hh, dd[8 * q], c.x);
+      c.y = __viaddmin_s16x2(hh, dd[8 * q + 2], c.y);
+      c.z = __viaddmin_s16x2(hh, dd[8 * q + 4], c.z);
+      c.w = __viaddmin_s16x2(hh, dd[8 * q + 6], c.w);
+      col[q] = c;
     }
   }
   // no trailing barrier: the next plane's barriers order its writes after these reads (see file header)
@@ -235,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
   const int o0 = p.origins[3 * n], o1 = p.origins[3 * n + 1], o2 = p.origins[3 * n + 2];
   const int cb0 = (o0 - RMAX) >> 5, cb1 = (o1 - RMAX) >> 5, cb2 = (o2 - RMAX) >> 5;
   const int xoff = (o2 - RMAX) - 32 * cb2;           // bit offset of the window start in data word 0
-  // ---- setup: cells of the window, zero pad words, distances = infinity
+  // ---- setup: cells of the window, zero pad words, table of squares, distances = infinity
   if (tid < NC) S.slab_any[tid] = 0;
   __syncthreads();
   for (int i = tid; i < NC * NC * NC; i += kThreads) {
@@ -247,10 +270,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
   for (int r = tid; r < EXT; r += kThreads) {
     S.rowbits[r][0] = 0; S.rowbits[r][1] = 0; S.rowbits[r][ROWW - 2] = 0; S.rowbits[r][ROWW - 1] = 0;
   }
-  {
-    uint32_t* d = reinterpret_cast<uint32_t*>(S.d2);
-    for (int i = tid; i < L * L * L / 2; i += kThreads) d[i] = 0xFFFFFFFFu;
+  for (int i = tid; i < SQ_N; i += kThreads) {
+    const int d = i - SQ_OFF;
+    S.sq2[i] = (uint32_t)(d * d) | ((uint32_t)((d + 1) * (d + 1)) << 16);
   }
+  for (int i = tid; i < L * L * D2P_PITCH; i += kThreads) S.d2p[i] = D2P_INF2;
   __syncthreads();
   const int R = min(max(p.max_radius, 0), RMAX);
   // ---- own planes
@@ -258,38 +282,40 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
   __syncthreads();
   // ---- largest squared distance so far bounds the remaining search radius
   uint32_t m = 0;
-  {
-    const uint32_t* d = reinterpret_cast<const uint32_t*>(S.d2);
-    for (int i = tid; i < L * L * L / 2; i += kThreads) {
-      const uint32_t v = d[i];
+  for (int c = tid; c < L * L; c += kThreads) {
+#pragma unroll
+    for (int w = 0; w < L / 2; ++w) {
+      const uint32_t v = S.d2p[c * D2P_PITCH + w];
       m = max(m, max(v & 0xFFFFu, v >> 16));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) S.red[tid >> 5] = m;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) S.red[tid >> 5] = m;
   __syncthreads();
   m = 0;
 #pragma unroll
   for (int w = 0; w < kThreads / 32; ++w) m = max(m, S.red[w]);
-  const int rlim = m >= D2_INF ? R : min(R, isqrt_floor(m));
+  const int rlim = m >= D2P_INF ? R : min(R, isqrt_floor(m));
   // ---- outer planes, nearest first
   for (int dz = 1; dz <= rlim; ++dz) {
     edt_plane(S, p, o0, o1, cb0, cb1, xoff, -dz, rlim);
     edt_plane(S, p, o0, o1, cb0, cb1, xoff, L - 1 + dz, rlim);
   }
   __syncthreads();
-  // ---- outputs
+  // ---- outputs, [i][j][k] order
   const size_t base = (size_t)n * (L * L * L);
   bool missing = false;
   for (int i = tid; i < L * L * L; i += kThreads) {
-    const uint32_t v = S.d2[i];
-    missing |= v >= D2_INF;
-    const double d = v >= D2_INF ? __longlong_as_double(0x7ff0000000000000ll) : sqrt((double)v);
+    const int sl = i >> 10, c = i & 1023;
+    uint32_t v = (S.d2p[c * D2P_PITCH + (sl >> 1)] >> (16 * (sl & 1))) & 0xFFFFu;
+    const bool none = v >= D2P_INF;
+    missing |= none;
+    const double d = none ? __longlong_as_double(0x7ff0000000000000ll) : sqrt((double)v);
     if (p.gt) p.gt[base + i] = v == 0 ? 1 : 0;
     if (p.dist64) p.dist64[base + i] = d;
     if (p.dist32) p.dist32[base + i] = (float)d;
-    if (p.d2) p.d2[base + i] = (uint16_t)v;
+    if (p.d2) p.d2[base + i] = none ? (uint16_t)D2_INF : (uint16_t)v;
   }
   if (missing) atomicOr(p.T.status, GRID_STATUS_NOT_FOUND);
 }
