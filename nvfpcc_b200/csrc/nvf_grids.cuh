@@ -124,17 +124,18 @@ struct EdtParams {
 
 // Squared distances live in shared memory as signed 16-bit halves of 32-bit words so that the two inner loops
 // run on the packed DPX instruction VIADDMNMX.S16x2 (min(a + b, c) on both halves at once):
-//   - all real values are <= 3 * 84^2 < 0x3FFF = D2P_INF, and D2P_INF + 84^2 < 2^15, so no sum overflows;
-//   - d2p[(j * 32 + k) * D2P_PITCH + (i >> 1)] holds slices i (low half, i even) and i + 1 of column (j, k):
-//     a thread's 32 slices are 16 consecutive words (4 x LDS.128); the pitch of 20 words makes the 128-bit
-//     accesses of the 32 lanes (consecutive k) bank-conflict free.
-constexpr int D2P_PITCH = 20;
+//   - all real values are <= 3 * 84^2 < 0x3FFF = D2P_INF, and D2P_INF + 87^2 < 2^15, so no sum overflows;
+//   - column (j, k) owns 16 consecutive words: word w holds slices 2w (low half) and 2w + 1.  A thread reads its
+//     32 slices with 4 x LDS.128; the 128-bit chunk q of column c sits at chunk q ^ ((k >> 1) & 3), which makes
+//     the accesses of the 32 lanes (consecutive k, 64-byte stride) bank-conflict free without padding.
 constexpr uint32_t D2P_INF = 0x3FFFu, D2P_INF2 = 0x3FFF3FFFu;
 constexpr int SQ_OFF = 85, SQ_N = 172;   // sq2[d + SQ_OFF] = pack(d^2, (d + 1)^2), d in [-85, 86]
 
 struct EdtSmem {
-  uint32_t d2p[L * L * D2P_PITCH];  // 80 KB running squared distances, see above
-  uint16_t g2[EXT][L];              // squared distance along a2 for the rows of the current plane (D2P_INF = none)
+  uint32_t d2p[L * L * (L / 2)];    // 64 KB running squared distances, see above
+  uint32_t g2c[EXT][L];             // per NON-EMPTY row n of the current plane (compact index): (g^2, g^2) packed,
+                                    // g = distance along a2 to the nearest set bit (D2P_INF = none)
+  uint32_t sqc[EXT][16];            // per non-empty row n and warp w: pack((4w - jrel)^2, (4w+1 - jrel)^2), pack((4w+2..)^2, (4w+3..)^2)
   uint32_t rowbits[EXT][ROWW];      // bit window of every row of the current plane
   uint32_t sq2[SQ_N];
   int32_t cellid[NC][NC][NC];
@@ -143,6 +144,7 @@ struct EdtSmem {
   int32_t nrows;
   uint32_t red[8];
 };
+__device__ __forceinline__ int d2p_chunk(int k, int q) { return q ^ ((k >> 1) & 3); }
 
 // 64 window bits starting at bit position b of a row (b + 64 <= 32 * ROWW)
 __device__ __forceinline__ unsigned long long row_bits64(const uint32_t* row, int b) {
@@ -194,30 +196,37 @@ __device__ __forceinline__ void edt_plane(EdtSmem& S, const EdtParams& p, int o0
   __syncthreads();
   const int nrows = S.nrows;
   if (nrows == 0) return;                            // uniform
-  // ---- (3) squared distance along a2 to the nearest set bit, for the 32 columns of the block
+  // ---- (3) squared distance along a2 to the nearest set bit, for the 32 columns of the block, stored per
+  //          compact row index; and the (j - row)^2 pairs every warp needs for that row
   for (int idx = tid; idx < nrows * L; idx += kThreads) {
-    const int r = S.rowlist[idx >> 5], k = idx & 31;
-    const uint32_t* row = S.rowbits[r];
+    const int n = idx >> 5, k = idx & 31;
+    const uint32_t* row = S.rowbits[S.rowlist[n]];
     const int c = 64 + xoff + RMAX + k;              // bit position of column k in the padded row
     const unsigned long long below = row_bits64(row, c - 63);   // bit 63 = position c
     const unsigned long long above = row_bits64(row, c);        // bit 0 = position c
     uint32_t g = 64;
     if (below) g = (uint32_t)__clzll((long long)below);
     if (above) g = min(g, (uint32_t)(__ffsll((long long)above) - 1));
-    S.g2[r][k] = g >= 64 ? (uint16_t)D2P_INF : (uint16_t)(g * g);
+    S.g2c[n][k] = (g >= 64 ? D2P_INF : g * g) * 0x10001u;
+  }
+  for (int idx = tid; idx < nrows * 16; idx += kThreads) {
+    const int n = idx >> 4, e = idx & 15;
+    S.sqc[n][e] = S.sq2[SQ_OFF + 2 * e - (S.rowlist[n] - RMAX)];      // rows j = 2e, 2e + 1
   }
   __syncthreads();
   // ---- (4) thread (k, rows j0..j0+3): h(j) = min over rows of g2 + (j - row)^2, two rows j per DPX instruction
-  const int k = tid & 31, j0 = (tid >> 5) * 4;
+  const int k = tid & 31, wid = tid >> 5, j0 = wid * 4;
   uint32_t h01 = D2P_INF2, h23 = D2P_INF2;
-  const uint32_t* sq = S.sq2 + SQ_OFF + j0 + RMAX;   // sq[-r] = pack((j0 - jrel)^2, (j0 + 1 - jrel)^2), jrel = r - RMAX
-#pragma unroll 2
-  for (int n = 0; n < nrows; ++n) {
-    const int r = S.rowlist[n];
-    const uint32_t v = S.g2[r][k];
-    const uint32_t vv = v * 0x10001u;
-    h01 = __viaddmin_s16x2(vv, sq[-r], h01);
-    h23 = __viaddmin_s16x2(vv, sq[2 - r], h23);
+  {
+    const uint32_t* gp = &S.g2c[0][k];
+    const uint2* sp = reinterpret_cast<const uint2*>(&S.sqc[0][2 * wid]);
+#pragma unroll 4
+    for (int n = 0; n < nrows; ++n) {
+      const uint32_t vv = gp[n * L];
+      const uint2 sq = sp[n * 8];
+      h01 = __viaddmin_s16x2(vv, sq.x, h01);
+      h23 = __viaddmin_s16x2(vv, sq.y, h23);
+    }
   }
   //      then d2(i) = min(d2(i), h + (i - prel)^2) for the slices within rlim of the plane, eight slices per LDS.128
   const int i_lo = max(0, prel - rlim), i_hi = min(L - 1, prel + rlim);
@@ -229,14 +238,14 @@ __device__ __forceinline__ void edt_plane(EdtSmem& S, const EdtParams& p, int o0
     const uint32_t ht = ((t < 2 ? h01 : h23) >> (16 * (t & 1))) & 0xFFFFu;
     if (ht >= D2P_INF) continue;
     const uint32_t hh = ht * 0x10001u;
-    uint4* col = reinterpret_cast<uint4*>(S.d2p + ((j0 + t) * L + k) * D2P_PITCH);
+    uint4* col = reinterpret_cast<uint4*>(S.d2p + ((j0 + t) * L + k) * (L / 2));
     for (int q = q_lo; q <= q_hi; ++q) {
-      uint4 c = col[q];
+      uint4 c = col[d2p_chunk(k, q)];
       c.x = __viaddmin_s16x2(hh, dd[8 * q], c.x);
       c.y = __viaddmin_s16x2(hh, dd[8 * q + 2], c.y);
       c.z = __viaddmin_s16x2(hh, dd[8 * q + 4], c.z);
       c.w = __viaddmin_s16x2(hh, dd[8 * q + 6], c.w);
-      col[q] = c;
+      col[d2p_chunk(k, q)] = c;
     }
   }
   // no trailing barrier: the next plane's barriers order its writes after these reads (see file header)
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
     const int d = i - SQ_OFF;
     S.sq2[i] = (uint32_t)(d * d) | ((uint32_t)((d + 1) * (d + 1)) << 16);
   }
-  for (int i = tid; i < L * L * D2P_PITCH; i += kThreads) S.d2p[i] = D2P_INF2;
+  for (int i = tid; i < L * L * (L / 2); i += kThreads) S.d2p[i] = D2P_INF2;
   __syncthreads();
   const int R = min(max(p.max_radius, 0), RMAX);
   // ---- own planes
@@ -282,12 +291,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
   __syncthreads();
   // ---- largest squared distance so far bounds the remaining search radius
   uint32_t m = 0;
-  for (int c = tid; c < L * L; c += kThreads) {
-#pragma unroll
-    for (int w = 0; w < L / 2; ++w) {
-      const uint32_t v = S.d2p[c * D2P_PITCH + w];
-      m = max(m, max(v & 0xFFFFu, v >> 16));
-    }
+  for (int i = tid; i < L * L * (L / 2); i += kThreads) {
+    const uint32_t v = S.d2p[i];
+    m = max(m, max(v & 0xFFFFu, v >> 16));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -308,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_edt_blocks(EdtParams p) {
   bool missing = false;
   for (int i = tid; i < L * L * L; i += kThreads) {
     const int sl = i >> 10, c = i & 1023;
-    uint32_t v = (S.d2p[c * D2P_PITCH + (sl >> 1)] >> (16 * (sl & 1))) & 0xFFFFu;
+    const int w = sl >> 1;
+    const uint32_t v = (S.d2p[c * (L / 2) + 4 * d2p_chunk(c & 31, w >> 2) + (w & 3)] >> (16 * (sl & 1))) & 0xFFFFu;
     const bool none = v >= D2P_INF;
     missing |= none;
     const double d = none ? __longlong_as_double(0x7ff0000000000000ll) : sqrt((double)v);
