@@ -276,21 +276,32 @@ __global__ void __launch_bounds__(ConvTDgradCfg<CG, CX, DIN, TY, CGC>::THREADS, 
       for (int j = 0; j < 4; ++j) acc2[a][c][j] = p2_bcast(0.f);
 
   const float* g_b = p.g + (size_t)b * CG * G::DG * G::DG * G::GP;
-  // two-stage cp.async pipeline over chunks of CGC gradient channels: chunk c+1 streams in while chunk c is consumed
+  // two-stage cp.async pipeline over chunks of CGC gradient channels: chunk c+1 streams in while chunk c is consumed.
+  // A thread copies the same tile positions for every chunk, so the (channel, slice, row, column) decomposition of
+  // its copy indices is done once here; per chunk only the channel offset is added.
+  constexpr int NV = G::GP / 4;
+  constexpr int NCOPY = CGC * 5 * G::GR * NV;
+  constexpr int PER_T = (NCOPY + G::THREADS - 1) / G::THREADS;
+  int soff[PER_T], goff[PER_T];
+#pragma unroll
+  for (int u = 0; u < PER_T; ++u) {
+    const int i = tid + u * G::THREADS;
+    int q = i < NCOPY ? i : 0;
+    const int cv = q % NV; q /= NV;
+    const int rr = q % G::GR; q /= G::GR;
+    const int s5 = q % 5; q /= 5;
+    const int c = q;
+    soff[u] = i < NCOPY ? ((c * 5 + s5) * G::GR + rr) * G::GPS + 4 * cv : -1;
+    goff[u] = ((c * G::DG + 2 * z + s5) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv;
+  }
   auto stage = [&](int chunk) {
     float* sg = smem + (chunk & 1) * G::STAGE;
     float* sw = sg + G::G_FLOATS;
     const int c0 = chunk * CGC;
-    constexpr int NV = G::GP / 4;
-    for (int i = tid; i < CGC * 5 * G::GR * NV; i += G::THREADS) {
-      int q = i;
-      const int cv = q % NV; q /= NV;
-      const int rr = q % G::GR; q /= G::GR;
-      const int s5 = q % 5; q /= 5;
-      const int c = q;
-      tma::cp_async16(sg + ((c * 5 + s5) * G::GR + rr) * G::GPS + 4 * cv,
-                      g_b + (((size_t)(c0 + c) * G::DG + 2 * z + s5) * G::DG + 2 * y0 + rr) * G::GP + 4 * cv);
-    }
+    const float* gc = g_b + (size_t)c0 * G::DG * G::DG * G::GP;
+#pragma unroll
+    for (int u = 0; u < PER_T; ++u)
+      if (soff[u] >= 0) tma::cp_async16(sg + soff[u], gc + goff[u]);
     const float* src = p.Wp + (size_t)c0 * 125 * CX;
     for (int i = tid; i < G::W_FLOATS / 4; i += G::THREADS) tma::cp_async16(sw + 4 * i, src + 4 * i);
   };
