@@ -540,7 +540,7 @@ struct DevLauncher {
     if (!smem_attr(fast::k_stem_fwd, smem)) return true;
     fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
                           nullptr, nullptr, x0, a0, a1, nullptr, nullptr, n, d.ch, d.c0, d.c1};
-    nvf_launch(fast::k_stem_fwd, dim3(n * 8), dim3(256), (size_t)(smem), st, q);
+    nvf_launch(fast::k_stem_fwd, dim3(n * 8), dim3(fast::kStemFwdThreads), (size_t)(smem), st, q);
     post();
     if (cls0) {   // conv0_cls + sigmoid: auxiliary head, off the critical path
       LayerParams p{a1, cls0, cls0_wp, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};
@@ -561,15 +561,15 @@ struct DevLauncher {
       partial = take_partial((size_t)n * pf);
       if (!partial) return false;
     }
-    const int smem_a = (d.c1 * 512 + 64 + 256 + d.c1 * 125) * (int)sizeof(float);
+    const int smem_a = (d.c1 * 512 + 64 + 512 + d.c1 * 125) * (int)sizeof(float);
     const int smem_b = (4 * d.c0 * 64 + d.ch * 8 + d.c0 * d.c0 + d.c0 + d.ch * d.c0 * 125) * (int)sizeof(float);
     if (smem_a > 200 * 1024 || smem_b > 200 * 1024) return false;
     if (!smem_attr(fast::k_stem_bwd_a, smem_a) || !smem_attr(fast::k_stem_bwd_b, smem_b)) return true;
     fast::StemBwdParams q{latent, x0, a0, g1, w.igdn_beta, w.igdn_gamma, w.conv0_w, w.up0_w, partial, g_latent,
                           n, d.ch, d.c0, d.c1, gw ? 1 : 0};
-    nvf_launch(fast::k_stem_bwd_a, dim3(n * d.c0), dim3(256), (size_t)(smem_a), st, q, gy0);
+    nvf_launch(fast::k_stem_bwd_a, dim3(n * d.c0), dim3(fast::kStemBwdAThreads), (size_t)(smem_a), st, q, gy0);
     post();
-    nvf_launch(fast::k_stem_bwd_b, dim3(n), dim3(256), (size_t)(smem_b), st, q, gy0);
+    nvf_launch(fast::k_stem_bwd_b, dim3(n), dim3(fast::kStemBwdBThreads), (size_t)(smem_b), st, q, gy0);
     post();
     if (gw) {
       const int n0 = d.c0 * d.c1 * 125, ng = d.c0 * d.c0, nu = d.ch * d.c0 * 125;

@@ -39,7 +39,8 @@ __device__ __forceinline__ int stem_tap_lo(int o) { return o & 1; }
 
 // grid = n * 8: CTA (b, zs) recomputes the tiny up0 + IGDN and produces conv0's output slice zs;
 // the conv0_cls head runs afterwards as a classifier kernel (nvf_fast_conv.cuh).
-__global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
+constexpr int kStemFwdThreads = 512;
+__global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
   pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
@@ -52,11 +53,11 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
   const int b = blockIdx.x >> 3, zs = blockIdx.x & 7, tid = threadIdx.x;
   const int pz = zs & 1, NT = pz ? 2 : 3;              // kz = pz + 2t
   if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
-  for (int i = tid; i < C0 * C0 + C0; i += 256) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
-  for (int i = tid; i < CH * 125 * C0; i += 256) s_wu[i] = __ldg(p.up0_wp + i);
+  for (int i = tid; i < C0 * C0 + C0; i += kStemFwdThreads) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
+  for (int i = tid; i < CH * 125 * C0; i += kStemFwdThreads) s_wu[i] = __ldg(p.up0_wp + i);
   {
     const int tapv = 25 * C1 / 4;   // float4 per (ci, kz)
-    for (int i = tid; i < C0 * 3 * tapv; i += 256) {
+    for (int i = tid; i < C0 * 3 * tapv; i += kStemFwdThreads) {
       const int v4 = i % tapv, t = (i / tapv) % 3, ci = i / (3 * tapv);
       if (t < NT)
         reinterpret_cast<float4*>(s_wc)[i] =
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
   }
   __syncthreads();
   // up0: CH x 2^3 -> C0 x 4^3
-  for (int idx = tid; idx < C0 * 64; idx += 256) {
+  for (int idx = tid; idx < C0 * 64; idx += kStemFwdThreads) {
     const int co = idx >> 6, z = (idx >> 4) & 3, y = (idx >> 2) & 3, x = idx & 3;
     float v = p.up0_b[co];
     for (int ci = 0; ci < CH; ++ci)
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
   }
   __syncthreads();
   // IGDN
-  for (int idx = tid; idx < C0 * 64; idx += 256) {
+  for (int idx = tid; idx < C0 * 64; idx += kStemFwdThreads) {
     const int c = idx >> 6, pos = idx & 63;
     float nn = s_gam[C0 * C0 + c];
     for (int j = 0; j < C0; ++j) {
@@ -100,9 +101,12 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
     if (zs == 0) p.a0[(size_t)b * C0 * 64 + idx] = v;
   }
   __syncthreads();
-  // conv0 slice zs: C0 x 4^3 -> C1 x 8 x 8, ReLU.  item = (position in the slice, group of 4 output channels)
+  // conv0 slice zs: C0 x 4^3 -> C1 x 8 x 8, ReLU.  item = (position in the slice, group of 4 output channels);
+  // the input-channel sum of an item is split over the two threads of a lane pair (halves the serial chain of
+  // this latency-bound kernel) and combined with one shuffle, always in the order (low half) + (high half).
   const int groups = C1 / 4;
-  for (int item = tid; item < 64 * groups; item += 256) {
+  const int half = tid & 1, ci_lo = half * (C0 / 2), ci_hi = ci_lo + C0 / 2;
+  for (int item = tid >> 1; item < 64 * groups; item += kStemFwdThreads / 2) {
     const int pos = item & 63, cg = item >> 6;
     const int z = zs, y = pos >> 3, x = pos & 7;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
           const int ipos = (tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1);
           const float* wk = s_wc + (size_t)(t * 25 + ky * 5 + kx) * C1 + cg * 4;
 #pragma unroll 4
-          for (int ci = 0; ci < C0; ++ci) {
+          for (int ci = ci_lo; ci < ci_hi; ++ci) {
             const float a = s_a0[ci * 64 + ipos];
             const float4 w0 = *reinterpret_cast<const float4*>(wk + (size_t)ci * 75 * C1);
             acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
@@ -129,8 +133,9 @@ __global__ void __launch_bounds__(256) k_stem_fwd(StemFwdParams p) {
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float v = acc[c] + p.conv0_b[cg * 4 + c];
-      p.a1[((size_t)b * C1 + cg * 4 + c) * 512 + zs * 64 + pos] = v > 0.f ? v : 0.f;
+      const float other = __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      const float v = (half ? other + acc[c] : acc[c] + other) + p.conv0_b[cg * 4 + c];
+      if (half == 0) p.a1[((size_t)b * C1 + cg * 4 + c) * 512 + zs * 64 + pos] = v > 0.f ? v : 0.f;
     }
   }
 }
@@ -156,27 +161,28 @@ __host__ __device__ inline int stem_partial_floats(int CH, int C0, int C1) {
 // Kernel A, grid = n * C0: CTA (b, ci) holds g1[b] in shared memory and produces
 //   conv0 wgrad rows dW[ci][:][:]  (per-block partial), the conv0 bias gradient (ci == 0),
 //   conv0 dgrad gy[b][ci][64] -> p.gy (global).
-__global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_out) {
+constexpr int kStemBwdAThreads = 512;   // these kernels are latency-bound chains: more threads = shorter chains
+__global__ void __launch_bounds__(kStemBwdAThreads) k_stem_bwd_a(StemBwdParams p, float* gy_out) {
   pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
   float* s_g1 = smem;                   // [C1][512]
   float* s_a0 = s_g1 + C1 * 512;        // [64]
-  float* s_part = s_a0 + 64;            // [4][64]
-  float* s_w = s_part + 256;            // conv0 W[ci][C1][125]
+  float* s_part = s_a0 + 64;            // [8][64]
+  float* s_w = s_part + 512;            // conv0 W[ci][C1][125]
   const int b = blockIdx.x / C0, ci = blockIdx.x % C0, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   {
     const float4* src = reinterpret_cast<const float4*>(p.g1 + (size_t)b * C1 * 512);
-    for (int i = tid; i < C1 * 128; i += 256) reinterpret_cast<float4*>(s_g1)[i] = __ldg(src + i);
+    for (int i = tid; i < C1 * 128; i += kStemBwdAThreads) reinterpret_cast<float4*>(s_g1)[i] = __ldg(src + i);
     if (tid < 64) s_a0[tid] = p.a0[((size_t)b * C0 + ci) * 64 + tid];
-    for (int i = tid; i < C1 * 125; i += 256) s_w[i] = __ldg(p.conv0_w + (size_t)ci * C1 * 125 + i);
+    for (int i = tid; i < C1 * 125; i += kStemBwdAThreads) s_w[i] = __ldg(p.conv0_w + (size_t)ci * C1 * 125 + i);
   }
   __syncthreads();
   float* part = p.partial ? p.partial + (size_t)b * stem_partial_floats(CH, C0, C1) : nullptr;
   if (p.need_w && part) {
     // conv0 wgrad: dW[ci][co][k] = sum_{i in 4^3} a0[ci][i] * g1[co][2i + k - 2]
-    for (int e = tid; e < C1 * 125; e += 256) {
+    for (int e = tid; e < C1 * 125; e += kStemBwdAThreads) {
       int q = e;
       const int kx = q % 5; q /= 5;
       const int ky = q % 5; q /= 5;
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
     }
     if (ci == 0) {
       // conv0 bias: one warp per channel, fixed-order shuffle tree
-      for (int co = warp; co < C1; co += 8) {
+      for (int co = warp; co < C1; co += kStemBwdAThreads / 32) {
         float s = 0.f;
         for (int i = lane; i < 512; i += 32) s += s_g1[co * 512 + i];
         for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -209,12 +215,12 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
       }
     }
   }
-  // conv0 dgrad: gy[ci][i] = sum_co sum_k g1[co][2i + k - 2] * W[ci][co][k]; co range split in 4 parts
+  // conv0 dgrad: gy[ci][i] = sum_co sum_k g1[co][2i + k - 2] * W[ci][co][k]; co range split in 8 parts
   {
     const int h = tid >> 6, e = tid & 63;
     const int iz = (e >> 4) & 3, iy = (e >> 2) & 3, ix = e & 3;
     float s = 0.f;
-    for (int co = h * (C1 / 4); co < (h + 1) * (C1 / 4); ++co) {
+    for (int co = h * (C1 / 8); co < (h + 1) * (C1 / 8); ++co) {
       const float* wk = s_w + co * 125;
       for (int kz = 0; kz < 5; ++kz) {
         const int oz = 2 * iz + kz - 2;
@@ -235,11 +241,13 @@ __global__ void __launch_bounds__(256) k_stem_bwd_a(StemBwdParams p, float* gy_o
   }
   __syncthreads();
   if (tid < 64)
-    gy_out[((size_t)b * C0 + ci) * 64 + tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
+    gy_out[((size_t)b * C0 + ci) * 64 + tid] = ((s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid])) +
+                                               ((s_part[256 + tid] + s_part[320 + tid]) + (s_part[384 + tid] + s_part[448 + tid]));
 }
 
 // Kernel B, grid = n: IGDN backward (dx, dbeta, dgamma), up0 wgrad / bias, d_latent.
-__global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float* gy_in) {
+constexpr int kStemBwdBThreads = 1024;
+__global__ void __launch_bounds__(kStemBwdBThreads) k_stem_bwd_b(StemBwdParams p, const float* gy_in) {
   pdl_entry();
   extern __shared__ __align__(128) float smem[];
   const int CH = p.CH, C0 = p.C0, C1 = p.C1;
@@ -252,19 +260,19 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   float* s_wu = s_gam + C0 * C0 + C0;   // up0 W (CH, C0, 125)
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < C0 * 64; i += 256) {
+  for (int i = tid; i < C0 * 64; i += kStemBwdBThreads) {
     s_x0[i] = p.x0[(size_t)b * C0 * 64 + i];
     s_gy[i] = gy_in[(size_t)b * C0 * 64 + i];
   }
   if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
-  for (int i = tid; i < C0 * C0 + C0; i += 256) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
+  for (int i = tid; i < C0 * C0 + C0; i += kStemBwdBThreads) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
   if (p.g_latent)
-    for (int i = tid; i < CH * C0 * 125; i += 256) s_wu[i] = __ldg(p.up0_w + i);
+    for (int i = tid; i < CH * C0 * 125; i += kStemBwdBThreads) s_wu[i] = __ldg(p.up0_w + i);
   __syncthreads();
   float* part = p.partial ? p.partial + (size_t)b * stem_partial_floats(CH, C0, C1) : nullptr;
   const int o_c0b = C0 * C1 * 125, o_gam = o_c0b + C1, o_bet = o_gam + C0 * C0, o_u0w = o_bet + C0,
             o_u0b = o_u0w + CH * C0 * 125;
-  for (int e = tid; e < C0 * 64; e += 256) {
+  for (int e = tid; e < C0 * 64; e += kStemBwdBThreads) {
     const int c = e >> 6, pos = e & 63;
     float nn = s_gam[C0 * C0 + c];
     for (int j = 0; j < C0; ++j) {
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   }
   __syncthreads();
   // IGDN backward: dx_k = g_k n_k + x_k sum_i g_i x_i gamma_ik / n_i
-  for (int e = tid; e < C0 * 64; e += 256) {
+  for (int e = tid; e < C0 * 64; e += kStemBwdBThreads) {
     const int k = e >> 6, pos = e & 63;
     float acc = 0.f;
     for (int i = 0; i < C0; ++i)
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   }
   if (p.need_w && part) {
     // dbeta_i = sum t_i, dgamma_ij = sum t_i x_j^2 with t_i = g_i x_i / (2 n_i)
-    for (int e = tid; e < C0 * C0 + C0; e += 256) {
+    for (int e = tid; e < C0 * C0 + C0; e += kStemBwdBThreads) {
       float s = 0.f;
       if (e < C0 * C0) {
         const int i = e / C0, j = e % C0;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   __syncthreads();
   if (p.need_w && part) {
     // up0 wgrad: dW[ci][co][k] = sum_{i in 2^3} lat[ci][i] * gx[co][2i + k - 2]
-    for (int e = tid; e < CH * C0 * 125; e += 256) {
+    for (int e = tid; e < CH * C0 * 125; e += kStemBwdBThreads) {
       int q = e;
       const int kx = q % 5; q /= 5;
       const int ky = q % 5; q /= 5;
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
       }
       part[o_u0w + e] = s;
     }
-    for (int co = warp; co < C0; co += 8) {
+    for (int co = warp; co < C0; co += kStemBwdBThreads / 32) {
       float s = s_gx[co * 64 + lane] + s_gx[co * 64 + 32 + lane];
       for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) part[o_u0b + co] = s;
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(256) k_stem_bwd_b(StemBwdParams p, const float
   }
   // d_latent[ci][i] = sum_co sum_k gx[co][2i + k - 2] * W[ci][co][k]: one warp per output, lanes over (co,k)
   if (p.g_latent) {
-    for (int e = warp; e < CH * 8; e += 8) {
+    for (int e = warp; e < CH * 8; e += kStemBwdBThreads / 32) {
       const int ci = e >> 3, i = e & 7;
       const int iz = i >> 2, iy = (i >> 1) & 1, ix = i & 1;
       float s = 0.f;
