@@ -149,7 +149,7 @@ int nvf_train_forward(const NvfDesc* desc, const NvfWeights* w, const float* lat
  *     NULL; when given they are the seeds nvf_train_backward consumes.
  */
 #define NVF_LOSS_SUMS 20
-#define NVF_LOSS_CHUNKS 8 /* workspace: sizeof(double) * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n_blocks + 1) bytes */
+#define NVF_LOSS_CHUNKS 16 /* workspace: sizeof(double) * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n_blocks + 1) bytes */
 int nvf_loss_seeds(const float* out, const float* cls1, const float* cls0, const float* gt, const float* dist,
                    int64_t n_blocks, float alpha_main, float alpha_aux, float thh_metric, double* sums_out,
                    float* g_out, float* g_cls1, float* g_cls0, void* workspace, size_t workspace_bytes,

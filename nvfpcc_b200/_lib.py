@@ -27,7 +27,7 @@ WEIGHT_FIELDS = (
 NVF_MODE_DECODE, NVF_MODE_TRAIN = 0, 1
 NVF_BWD_WGRAD, NVF_BWD_DLATENT = 1, 2
 NVF_LOSS_SUMS = 20
-NVF_LOSS_CHUNKS = 8   # CTAs per block of nvf_loss_seeds (workspace: 8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1) bytes)
+NVF_LOSS_CHUNKS = 16   # CTAs per block of nvf_loss_seeds (workspace: 8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1) bytes)
 EXPORTS = (
     "nvf_abi_version", "nvf_strerror", "nvf_last_cuda_error", "nvf_launch_count", "nvf_has_fused_decode", "nvf_workspace_bytes",
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",

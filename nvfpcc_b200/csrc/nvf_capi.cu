@@ -81,7 +81,7 @@ struct DevEnv {
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(kThreads) k_pack(PackParams p) {
   pdl_entry();
-  pack_thread(p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  pack_thread(p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, (int)blockIdx.y);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_decode_fused_A(FusedAParams p) {
@@ -267,7 +267,11 @@ struct DevLauncher {
   int sms() const { return n_sms; }
   int error() const { return rc; }
 
-  void pack(const PackParams& p) { nvf_launch(k_pack, dim3(n_sms > 0 ? n_sms : 32), dim3(kThreads), (size_t)(0), st, p); post(); }
+  void pack(const PackParams& p) {
+    if (p.njobs <= 0) return;
+    nvf_launch(k_pack, dim3(32, p.njobs), dim3(kThreads), (size_t)(0), st, p);   // one grid row per job
+    post();
+  }
   void fusedA(const FusedAParams& p, int grid) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -203,8 +203,10 @@ struct PackParams {
   int32_t njobs;
 };
 
-NVF_HD void pack_thread(const PackParams& p, int gtid, int gthreads) {
-  for (int j = 0; j < p.njobs; ++j) {
+// only_job >= 0: this thread works on that job alone (the GPU launches one grid row per job, so the jobs'
+// load -> store latencies overlap instead of adding up)
+NVF_HD void pack_thread(const PackParams& p, int gtid, int gthreads, int only_job = -1) {
+  for (int j = (only_job >= 0 ? only_job : 0); j < (only_job >= 0 ? only_job + 1 : p.njobs); ++j) {
     const PackJob& J = p.job[j];
     const int K3 = J.K * J.K * J.K;
     const int n = J.A * J.B * K3;

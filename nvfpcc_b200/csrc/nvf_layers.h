@@ -349,7 +349,7 @@ NVF_HD void focal_term(float p, bool occ, float a_occ, float a_emp, float w, flo
   dldp = clamped ? 0.f : (occ ? dF : -dF);
 }
 
-constexpr int kLossChunks = 8;  // CTAs per block: chunk c covers main-head slices 4c..4c+3 and the aux voxels below them
+constexpr int kLossChunks = 16;  // CTAs per block: chunk c covers main-head slices 2c, 2c+1 and the aux voxels below them
 struct LossBlock {
   // smem: kThreads * NVF_LOSS_SUMS doubles
   template <class Env>
