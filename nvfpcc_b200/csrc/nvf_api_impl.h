@@ -307,7 +307,7 @@ struct Api {
                   thh_metric, (int32_t)n};
     l.loss(lp, (int)n * kLossChunks);
     LossFinalKernel::Params fp{(const double*)workspace, sums_out, (int32_t)n * kLossChunks};
-    l.template generic<LossFinalKernel>(fp, 1);
+    l.template generic<LossFinalKernel>(fp, LossFinalKernel::kGrid);
     return l.error();
   }
 

@@ -426,11 +426,24 @@ struct LossFinalKernel {
     double* sums;
     int32_t n;
   };
+  // launched with kGrid CTAs: one warp per sum, lanes stride over the partials, fixed-order shuffle tree
+  // (deterministic; a single thread per sum was a serial chain of n dependent double adds - 20 k of them
+  // in the full-batch embedding step)
+  static constexpr int kGrid = (NVF_LOSS_SUMS * 32 + kThreads - 1) / kThreads;
   static NVF_HD void thread(const Params& p, int bid, int tid, int nbid) {
+#if defined(__CUDA_ARCH__)
+    const int w = (bid * kThreads + tid) >> 5, lane = tid & 31;
+    if (w >= NVF_LOSS_SUMS) return;
+    double s = 0.0;
+    for (int b = lane; b < p.n; b += 32) s += p.partial[(int64_t)b * NVF_LOSS_SUMS + w];
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) p.sums[w] = s;
+#else
     if (bid != 0 || tid >= NVF_LOSS_SUMS) return;
     double s = 0.0;
     for (int b = 0; b < p.n; ++b) s += p.partial[(int64_t)b * NVF_LOSS_SUMS + tid];
     p.sums[tid] = s;
+#endif
   }
 };
 
