@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(ConvTFwdCfg<CI, CO, DIN, KS>::THREADS, MINB) k
   for (int ci = kgrp * (CI / KS); ci < (active ? (kgrp + 1) * (CI / KS) : 0); ++ci) {
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
+      // input slice of this tap outside the tensor (first / last output slices): all zeros, nothing to add (uniform)
+      const int iz_t = ((z - pz) >> 1) - t;
+      if (iz_t < 0 || iz_t >= DIN) continue;
       // tile rows 2rg .. 2rg+3  (iy = 2rg-2 .. 2rg+1), columns 4q+2 .. 4q+7  (ix = 4q-2 .. 4q+3)
       const float* base = s_in + ((ci * 3 + t) * G::TR + 2 * rg) * G::IP + 4 * q + 2;
       p2 R[4][6];
