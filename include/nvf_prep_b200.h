@@ -49,6 +49,17 @@ int nvf_build_grids(const int32_t* points, int64_t n_points, const int32_t* orig
                     uint16_t* d2_out, int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Minibatch gather for device-resident datasets.  Replaces the DataLoader batch assembly +
+ * `.to(device)` + `emb[indices]` of the weight loop (LoadedVoxelDataset.__getitem__,
+ * utils/dataloader.py:163-172; NVFPCC.py:151-158) when gt / dist / emb already live in HBM:
+ * ONE launch copies the rows `idx` of the three tensors into the step's static input buffers.
+ *   emb_all [N, emb_floats], gt_all / dist_all [N, 32768] float32, idx [n] int64 (device),
+ *   emb_out [n, emb_floats], gt_out / dist_out [n, 32768].  Indices must lie in [0, N).
+ */
+int nvf_gather_batch(const float* emb_all, const float* gt_all, const float* dist_all, const int64_t* idx,
+                     int64_t n, int32_t emb_floats, float* emb_out, float* gt_out, float* dist_out, void* stream);
+
+/*
  * Latent bitstream: the arithmetic code of the rounded latents.  Replaces the
  * `./module_arithmeticcoding e|d 1 1` subprocess of encode()/decode() (NVFPCC.py:446-477,
  * 588-607; module_arithmeticcoding.cpp:368-432) with an in-process call producing / consuming

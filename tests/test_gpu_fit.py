@@ -52,3 +52,16 @@ def test_fit_trains_checkpoints_and_round_trips(gpu, tmp_path):
     network.set_seed(synth.synthetic_seed())
     dec = codec.decode(enc["total_pack"], 3, "8,16,8,8", 0.5)
     assert np.array_equal(dec, enc["points"])
+
+
+def test_gather_batch_equals_indexing(gpu):
+    from nvfpcc_b200 import trainer
+    g = torch.Generator().manual_seed(3)
+    n_all, n = 57, 16
+    emb = torch.randn(n_all, 3, 2, 2, 2, generator=g).cuda()
+    gt = (torch.rand(n_all, 1, 32, 32, 32, generator=g) < 0.05).float().cuda()
+    dist = torch.rand(n_all, 1, 32, 32, 32, generator=g).cuda()
+    idx = torch.randint(0, n_all, (n,), generator=g).cuda()
+    e, a, d = torch.zeros(n, 3, 2, 2, 2).cuda(), torch.zeros(n, 1, 32, 32, 32).cuda(), torch.zeros(n, 1, 32, 32, 32).cuda()
+    trainer._gather_batch(emb, gt, dist, idx, e, a, d)
+    assert torch.equal(e, emb[idx]) and torch.equal(a, gt[idx]) and torch.equal(d, dist[idx])

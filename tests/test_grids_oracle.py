@@ -75,9 +75,9 @@ def declared_functions():
 
 
 def test_prep_header_symbols_are_exported_and_bound():
-    from nvfpcc_b200 import build, entropy, grids
+    from nvfpcc_b200 import build, entropy, grids, trainer
     names = declared_functions()
-    assert sorted(grids.EXPORTS + entropy.EXPORTS) == names
+    assert sorted(grids.EXPORTS + entropy.EXPORTS + trainer.EXPORTS) == names
     lib = ctypes.CDLL(build.build())
     for n in names:
         assert hasattr(lib, n), n
