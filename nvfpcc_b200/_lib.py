@@ -270,7 +270,7 @@ class Binding:
         dev = out.device
         n = int(out.shape[0])
         ts = [t.detach().contiguous().float() for t in (out, cls1, cls0, gt, dist)]
-        sums = torch.zeros((NVF_LOSS_SUMS,), dtype=torch.float64, device=dev)
+        sums = torch.empty((NVF_LOSS_SUMS,), dtype=torch.float64, device=dev)   # every entry is written by the finalisation
         ws = self.cached_workspace(8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1), dev, "loss")
         g = [torch.empty_like(t) for t in ts[:3]] if want_seeds else [None, None, None]
         rc = self.lib.nvf_loss_seeds(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), n,

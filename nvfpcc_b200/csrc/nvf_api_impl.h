@@ -341,15 +341,15 @@ struct Api {
     const bool wg = (flags & NVF_BWD_WGRAD) != 0;
     // the heads' probabilities were kept by nvf_train_forward: dL/dlogit = dL/dp * p (1 - p)
     LayerParams p{};
-    auto sig = [&](const float* gp, const float* prob, float* buf, int64_t cnt) {
-      SigBwdParams sp{gp, prob, buf, cnt};
-      int grid = (int)((cnt + kThreads - 1) / kThreads);
+    {
+      SigBwd3Params sp{{g_out, g_cls1, g_cls0},
+                       {(const float*)(ws + W.off_p2), (const float*)(ws + W.off_p1), (const float*)(ws + W.off_p0)},
+                       {gl2, gl1, gl0},
+                       {(int64_t)n * kVox, (int64_t)n * 4096, (int64_t)n * 512}};
+      int64_t grid = ((int64_t)n * (kVox + 4096 + 512) + kThreads - 1) / kThreads;
       if (grid > 4096) grid = 4096;
-      l.template generic<SigBwdKernel>(sp, grid);
-    };
-    sig(g_out, (const float*)(ws + W.off_p2), gl2, (int64_t)n * kVox);
-    sig(g_cls1, (const float*)(ws + W.off_p1), gl1, (int64_t)n * 4096);
-    sig(g_cls0, (const float*)(ws + W.off_p0), gl0, (int64_t)n * 512);
+      l.template generic<SigBwd3Kernel>(sp, (int)grid);
+    }
 
     // ---- conv2_cls ----
     if (wg) {

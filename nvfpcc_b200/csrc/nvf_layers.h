@@ -281,6 +281,26 @@ struct SigBwdKernel {
   }
 };
 
+// the three heads in one launch: segment h covers n[h] elements
+struct SigBwd3Params {
+  const float* gp[3];
+  const float* p[3];
+  float* out[3];
+  int64_t n[3];
+};
+struct SigBwd3Kernel {
+  typedef SigBwd3Params Params;
+  static NVF_HD void thread(const SigBwd3Params& q, int bid, int tid, int nbid) {
+    const int64_t total = q.n[0] + q.n[1] + q.n[2];
+    for (int64_t t = (int64_t)bid * kThreads + tid; t < total; t += (int64_t)nbid * kThreads) {
+      const int h = t < q.n[0] ? 0 : (t < q.n[0] + q.n[1] ? 1 : 2);
+      const int64_t i = t - (h == 0 ? 0 : (h == 1 ? q.n[0] : q.n[0] + q.n[1]));
+      const float pr = q.p[h][i];
+      q.out[h][i] = q.gp[h] ? q.gp[h][i] * pr * (1.f - pr) : 0.f;
+    }
+  }
+};
+
 // probability grid -> occupancy mask words + per-block counts (generic decode path)
 struct MaskParams {
   const float* prob;  // [n][32768]
