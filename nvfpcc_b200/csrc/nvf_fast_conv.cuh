@@ -545,8 +545,21 @@ __global__ void __launch_bounds__(256) k_reduce_partials(ReduceParams p) {
   for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
     const int i = i0 + lane;
     float s = 0.f;
-    if (i < n)
-      for (int c = part; c < J.count; c += 8) s += J.partial[(size_t)c * J.stride + i];
+    if (i < n) {
+      // four independent running sums keep four loads in flight (the loop is L2-latency bound); the order
+      // of the additions is fixed, so the result is deterministic
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* src = J.partial + i;
+      int c = part;
+      for (; c + 24 < J.count; c += 32) {
+        s0 += src[(size_t)c * J.stride];
+        s1 += src[(size_t)(c + 8) * J.stride];
+        s2 += src[(size_t)(c + 16) * J.stride];
+        s3 += src[(size_t)(c + 24) * J.stride];
+      }
+      for (; c < J.count; c += 8) s0 += src[(size_t)c * J.stride];
+      s = (s0 + s1) + (s2 + s3);
+    }
     sm[part][lane] = s;
     __syncthreads();
     if (part == 0 && i < n) {
