@@ -217,7 +217,7 @@ class TrainWorkload:
         self.n_total = float(pts.shape[0])
         self.gt_dev = g["gt"].float()
         self.dist_dev = g["dist32"]
-        self.gt_host = self.gt_dev.cpu().pin_memory()
+        self.gt_host = g["gt"].cpu().pin_memory()          # uint8, as *_gt_grid.npy stores it; converted on the device
         self.dist_host = self.dist_dev.cpu().pin_memory()
         self.nb = nb
         self.net = make_net(args.chanstr, "cuda")
@@ -264,7 +264,7 @@ class TrainWorkload:
                 self.last_loss = float(prev[0])
         self.last_loss = float(f.drain()[0])
 
-    h2d_bytes = 2 * 16 * 32768 * 4
+    h2d_bytes = 16 * 32768 * (1 + 4)      # gt uint8 + dist float32 per block
     d2h_bytes = 7 * 4
 
 
