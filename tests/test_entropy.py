@@ -162,3 +162,42 @@ def test_quantize_state_and_ply_writer(tmp_path):
     pts = np.array([[1, 2, 3], [1023, 0, 77]], dtype=np.int32)
     codec.write_ply_ascii(str(tmp_path / "a.ply"), pts)
     assert np.array_equal(grids.read_ply_xyz(str(tmp_path / "a.ply")), pts.astype(np.float64))
+
+
+# ----------------------------------------------------------------------------- property tests
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(0, 300), st.floats(0.003, 40.0), st.floats(-30.0, 30.0))
+def test_arithmetic_round_trip_property(seed, n, sigma_scale, mu_shift):
+    """Any symbol sequence in range round-trips under any per-symbol Gaussian parameters; when the compiled
+    reference helper is present the stream is also byte-identical to its output."""
+    rng = np.random.default_rng(seed)
+    mu = (512 + mu_shift + rng.normal(0, 5, n)).astype(np.float32)
+    sg = (np.abs(rng.normal(0, sigma_scale, n)) + 1e-3).astype(np.float32)
+    sym = np.clip(np.rint(rng.normal(mu, np.minimum(sg * 2, 200))), 0, 1023).astype(np.int16)
+    stream = entropy.arithmetic_encode(sym, mu, sg)
+    assert np.array_equal(entropy.arithmetic_decode(stream, mu, sg), sym)
+    if os.path.isfile(REF_EXE):
+        length = np.array([n], dtype=np.int64)
+        ref = sp.run([REF_EXE, "e", "1", "1"], input=length.tobytes() + sym.tobytes() + mu.tobytes() + sg.tobytes(),
+                     stdout=sp.PIPE).stdout
+        assert stream == ref
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 400), st.floats(0.2, 12.0))
+def test_huffman_round_trip_property(seed, n, spread):
+    rng = np.random.default_rng(seed)
+    pool = [np.rint(rng.laplace(0, spread, size=(n,))).astype(np.float32), np.rint(rng.normal(0, spread, size=(3, 5))).astype(np.float32)]
+    eles = np.concatenate([p.reshape(-1) for p in pool])
+    pdf, bins = entropy.get_pdf(eles)
+    codebook, inv = entropy.get_huffman_codebook(pdf, bins)
+    assert len(set(inv.keys())) == len(inv) == len(pdf)
+    words = sorted(inv.keys())
+    assert not any(b.startswith(a) for a, b in zip(words, words[1:]))          # prefix free
+    stream, shapes = entropy.entropy_encode(pool, codebook)
+    assert len(stream) == (sum(len(codebook[int(v)]) for v in eles) + 7) // 8
+    dec = entropy.entropy_decode(stream, inv, len(eles), shapes)
+    assert all(np.array_equal(a, b) for a, b in zip(pool, dec))
