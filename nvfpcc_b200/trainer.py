@@ -404,6 +404,7 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
     if ws > 1:                                                                      # same step count on every rank
         steps = (D.block_range(n_leaf_all, 0, ws)[1] + B - 1) // B                  # rank 0 holds the longest range
     order = torch.tensor([dataset_index(i, n_leaf, dataset_shuffle) for i in range(n_leaf)], device=dev)
+    batches = [order[(torch.arange(B, device=dev) + s * B) % n_leaf].contiguous() for s in range(steps)]   # built once
     history = []
     acc = torch.zeros(len(STAT_NAMES), device=dev)
     q = 1 if start_epoch < phase_change else 2
@@ -412,8 +413,7 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
             q = 2
         acc.zero_()
         for s in range(steps):
-            idx = order[(torch.arange(B, device=dev) + s * B) % n_leaf]
-            st = wstep.step_indexed(emb_local, gt_d, dist_d, idx, q=q)
+            st = wstep.step_indexed(emb_local, gt_d, dist_d, batches[s], q=q)
             acc += st
         est = estep.step(gt_d, dist_d, q)
         with warnings.catch_warnings():          # the graph replays opt.step(); the schedulers cannot see it
