@@ -148,6 +148,8 @@ def dist_setup(n_gpus):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints one) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
