@@ -41,6 +41,24 @@ FP32_PEAK_THEORETICAL = 148 * 128 * 2 * 1.965e9 / 1e12   # TFLOP/s at the 1965 M
 HP = dict(lmbda=200.0, w1=10.0, w2=57.0, lr=1e-3, batch=16, thh=0.65)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on rank 0),
+    so keep a private duplicate of the real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,8 +166,6 @@ def dist_setup(n_gpus):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints one) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -625,7 +641,7 @@ def run_reference(args):
                             e2e=dict(value=dec["value"], unit="voxels/s", h2d_bytes_per_step=0,
                                      d2h_bytes_per_step=0)),
                 grids=grids_ref, codec=dict(entropy=entropy_ref))
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -640,6 +656,7 @@ def workload_config(args, world):
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     from nvfpcc_b200 import _lib
@@ -770,7 +787,7 @@ def main():
         line["torch_cuda_baseline"] = torch_cuda_baseline(args, pts, origins)
         line["cpu_baseline"], _ = cpu_train_baseline(args, pts, origins, budget_s=15.0)
         line["decode"]["cpu_baseline"] = cpu_decode_baseline(args, origins, budget_s=10.0)
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":
