@@ -248,7 +248,9 @@ __device__ __forceinline__ void edt_plane(EdtSmem& S, const EdtParams& p, int o0
       col[d2p_chunk(k, q)] = c;
     }
   }
-  // no trailing barrier: the next plane's barriers order its writes after these reads (see file header)
+  // no trailing barrier: the next plane writes rowbits in its step (1), which nobody reads after the barrier that ended
+  // step (3) above, and touches rowlist / g2c / sqc only after its own first barrier, which every thread reaches after
+  // finishing this step; the d2p columns are private to their thread.
 }
 
 __device__ __forceinline__ int isqrt_floor(uint32_t v) {
