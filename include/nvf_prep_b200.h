@@ -53,11 +53,15 @@ int nvf_build_grids(const int32_t* points, int64_t n_points, const int32_t* orig
  * `.to(device)` + `emb[indices]` of the weight loop (LoadedVoxelDataset.__getitem__,
  * utils/dataloader.py:163-172; NVFPCC.py:151-158) when gt / dist / emb already live in HBM:
  * ONE launch copies the rows `idx` of the three tensors into the step's static input buffers.
- *   emb_all [N, emb_floats], gt_all / dist_all [N, 32768] float32, idx [n] int64 (device),
- *   emb_out [n, emb_floats], gt_out / dist_out [n, 32768].  Indices must lie in [0, N).
+ *   emb_all [n_rows, emb_floats], gt_all / dist_all [n_rows, 32768] float32, idx [n] int64 (device),
+ *   emb_out [n, emb_floats], gt_out / dist_out [n, 32768].
+ *   status  optional device int32 (sticky): bit 0 is set when an index lies outside [0, n_rows) - that row is
+ *           then read from row 0 instead of out of bounds (the indices live on the device, so the host cannot
+ *           check them without a synchronisation; callers read the word when they read their results).
  */
 int nvf_gather_batch(const float* emb_all, const float* gt_all, const float* dist_all, const int64_t* idx,
-                     int64_t n, int32_t emb_floats, float* emb_out, float* gt_out, float* dist_out, void* stream);
+                     int64_t n, int64_t n_rows, int32_t emb_floats, float* emb_out, float* gt_out, float* dist_out,
+                     int32_t* status, void* stream);
 
 /*
  * Latent bitstream: the arithmetic code of the rounded latents.  Replaces the

@@ -158,7 +158,9 @@ class Binding:
         return int(out.value)
 
     def cached_workspace(self, nbytes: int, dev: torch.device, tag: str) -> torch.Tensor:
-        """Grow-only scratch buffer per (device, tag); contents need not survive between calls."""
+        """Grow-only scratch buffer per (device, tag); contents need not survive between calls.  Only for calls
+        whose size is fixed (parameter-side kernels) or that are never captured in a CUDA graph (decode): a
+        superseded buffer is dropped, so its address must not outlive the call."""
         key = (str(dev), tag)
         buf = self._ws.get(key)
         if buf is None or buf.numel() < nbytes:
@@ -271,7 +273,10 @@ class Binding:
         n = int(out.shape[0])
         ts = [t.detach().contiguous().float() for t in (out, cls1, cls0, gt, dist)]
         sums = torch.empty((NVF_LOSS_SUMS,), dtype=torch.float64, device=dev)   # every entry is written by the finalisation
-        ws = self.cached_workspace(8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1), dev, "loss")
+        # owned by this call: the pointer is baked into captured CUDA graphs (trainer.WeightStep), so it must not come
+        # from the shared grow-only cache, which drops a buffer when a later, larger call (the full-batch embedding
+        # step) outgrows it.  Inside a capture the allocation comes from the graph's private pool and stays valid.
+        ws = torch.empty(8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1), dtype=torch.uint8, device=dev)
         g = [torch.empty_like(t) for t in ts[:3]] if want_seeds else [None, None, None]
         rc = self.lib.nvf_loss_seeds(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(ts[4]), n,
                                      float(alpha_main), float(alpha_aux), float(thh_metric), _ptr(sums), _ptr(g[0]),
@@ -438,6 +443,12 @@ class Binding:
 
     def launch_count(self) -> int:
         return int(self.lib.nvf_launch_count())
+
+    def has_fused_decode(self, chanstr) -> bool:
+        """True when nvf_decode runs the fused per-block kernel for this channel configuration (ch = 3)."""
+        ch = [int(c) for c in chanstr.split(",")] if isinstance(chanstr, str) else list(chanstr)
+        d = self.desc(3, ch)
+        return bool(self.lib.nvf_has_fused_decode(C.byref(d)))
 
     def ffma_microbench(self, variant: int, iters: int, sink: torch.Tensor) -> float:
         flops = C.c_double(0)

@@ -50,14 +50,21 @@ struct Chk {
   }
 };
 
-// rows idx[b] of gt / dist (32768 floats each) and of emb -> static batch buffers; grid (n, 16)
+// rows idx[b] of gt / dist (32768 floats each) and of emb -> static batch buffers; grid (n, 16).
+// An index outside [0, n_rows) is clamped to row 0 and reported through the sticky status word.
 __global__ void __launch_bounds__(256) k_gather_batch(const float* __restrict__ emb_all, const float4* __restrict__ gt_all,
                                                       const float4* __restrict__ dist_all, const int64_t* __restrict__ idx,
-                                                      int emb_floats, float* __restrict__ emb_out,
-                                                      float4* __restrict__ gt_out, float4* __restrict__ dist_out) {
+                                                      int64_t n_rows, int emb_floats, float* __restrict__ emb_out,
+                                                      float4* __restrict__ gt_out, float4* __restrict__ dist_out,
+                                                      int32_t* __restrict__ status) {
   pdl_entry();
   const int b = blockIdx.x, part = blockIdx.y;
-  const size_t src = (size_t)idx[b] * 8192, dst = (size_t)b * 8192;
+  int64_t row = idx[b];
+  if (row < 0 || row >= n_rows) {
+    if (status && part == 0 && threadIdx.x == 0) atomicOr(status, 1);
+    row = 0;
+  }
+  const size_t src = (size_t)row * 8192, dst = (size_t)b * 8192;
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int i = part * 512 + u * 256 + threadIdx.x;
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(256) k_gather_batch(const float* __restrict__ 
   }
   if (part == 0)
     for (int i = threadIdx.x; i < emb_floats; i += 256)
-      emb_out[(size_t)b * emb_floats + i] = emb_all[(size_t)idx[b] * emb_floats + i];
+      emb_out[(size_t)b * emb_floats + i] = emb_all[(size_t)row * emb_floats + i];
 }
 
 }  // namespace
@@ -74,14 +81,16 @@ __global__ void __launch_bounds__(256) k_gather_batch(const float* __restrict__ 
 extern "C" {
 
 int nvf_gather_batch(const float* emb_all, const float* gt_all, const float* dist_all, const int64_t* idx, int64_t n,
-                     int32_t emb_floats, float* emb_out, float* gt_out, float* dist_out, void* stream) {
-  if (n < 0 || n > 0x7fffffff || emb_floats < 1 || !emb_all || !gt_all || !dist_all || !idx || !emb_out || !gt_out ||
-      !dist_out)
+                     int64_t n_rows, int32_t emb_floats, float* emb_out, float* gt_out, float* dist_out,
+                     int32_t* status, void* stream) {
+  if (n < 0 || n > 0x7fffffff || n_rows < 1 || emb_floats < 1 || !emb_all || !gt_all || !dist_all || !idx || !emb_out ||
+      !gt_out || !dist_out)
     return NVF_ERR_INVALID_ARG;
   if (n == 0) return NVF_OK;
   Chk chk;
   k_gather_batch<<<dim3((unsigned)n, 16), 256, 0, (cudaStream_t)stream>>>(
-      emb_all, (const float4*)gt_all, (const float4*)dist_all, idx, emb_floats, emb_out, (float4*)gt_out, (float4*)dist_out);
+      emb_all, (const float4*)gt_all, (const float4*)dist_all, idx, n_rows, emb_floats, emb_out, (float4*)gt_out,
+      (float4*)dist_out, status);
   chk.launched();
   return chk.rc;
 }

@@ -174,10 +174,10 @@ class _RdTotalFn(torch.autograd.Function):
     (NVFPCC.py:161-164,196); backward in one launch."""
 
     @staticmethod
-    def forward(ctx, sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2):
+    def forward(ctx, sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2, w2_grad):
         b = _lib.cuda_binding()
         loss, stats = b.rd_total(sums, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2)
-        ctx.consts = (n_total, lmbda, w1, w2)
+        ctx.consts = (n_total, lmbda, w1, w2_grad)
         ctx.save_for_backward(n_pts)
         ctx.mark_non_differentiable(stats)
         return loss.reshape(()), stats
@@ -187,14 +187,18 @@ class _RdTotalFn(torch.autograd.Function):
         b = _lib.cuda_binding()
         (n_pts,) = ctx.saved_tensors
         g_dist, g_lb, g_nb = b.rd_total_backward(g_loss, n_pts, *ctx.consts)
-        return None, g_dist[0], g_dist[1], g_dist[2], g_lb.reshape(()), g_nb, None, None, None, None, None
+        return None, g_dist[0], g_dist[1], g_dist[2], g_lb.reshape(()), g_nb, None, None, None, None, None, None
 
 
-def rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total: float, lmbda: float, w1: float, w2: float):
+def rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total: float, lmbda: float, w1: float, w2: float,
+             w2_grad=None):
     """-> (loss, stats[7] = loss bce ms0 ms1 b_latent b_net n_pts).  `sums`/`bce`/`ms0`/`ms1` as returned by
-    rd_distortion (the three scalars only carry the autograd edges; values are read from `sums`)."""
+    rd_distortion (the three scalars only carry the autograd edges; values are read from `sums`).
+    w2_grad: weight of the network-rate term in the BACKWARD pass only (default w2).  Data-parallel training sums
+    the ranks' gradients, and the network-rate term lmbda*w2*sum(net_bits)/n_total does not depend on the rank's
+    blocks: it must enter the summed gradient once, so every rank but one passes 0 (trainer._loss_terms)."""
     return _RdTotalFn.apply(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, float(n_total), float(lmbda),
-                            float(w1), float(w2))
+                            float(w1), float(w2), float(w2 if w2_grad is None else w2_grad))
 
 
 RAW_FIELDS = tuple("%s_%s" % (l, f) for l in _lib.CONV_LAYERS for f in ("kernel", "kernel_init", "b", "b_init")) + (

@@ -29,18 +29,25 @@ EXPORTS = ("nvf_gather_batch",)          # include/nvf_prep_b200.h entry points 
 _gather_bound = None
 
 
-def _gather_batch(emb_all, gt_all, dist_all, idx, emb_out, gt_out, dist_out) -> None:
-    """nvf_gather_batch: rows `idx` of the three device-resident tensors -> the static batch buffers, one launch."""
+def _gather_batch(emb_all, gt_all, dist_all, idx, emb_out, gt_out, dist_out, status=None) -> None:
+    """nvf_gather_batch: rows `idx` of the three device-resident tensors -> the static batch buffers, one launch.
+    status: optional int32 device word; bit 0 is set by the kernel when an index is out of range."""
     import ctypes as C
     global _gather_bound
     b = ops._lib.cuda_binding()
     if _gather_bound is None:
         vp = C.c_void_p
-        b.lib.nvf_gather_batch.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
+        b.lib.nvf_gather_batch.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]
         _gather_bound = b
+    n_rows = int(gt_all.shape[0])
+    for t, per_row in ((emb_all, int(emb_out[0].numel())), (gt_all, 32768), (dist_all, 32768)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == n_rows and
+                t[0].numel() == per_row):
+            raise ops.NvfError("nvf_gather_batch needs contiguous float32 CUDA tensors with %d rows" % n_rows)
     p = ops._lib._ptr
-    rc = b.lib.nvf_gather_batch(p(emb_all), p(gt_all), p(dist_all), p(idx), int(idx.numel()), int(emb_all[0].numel()),
-                                p(emb_out), p(gt_out), p(dist_out), b._stream(gt_all.device))
+    rc = b.lib.nvf_gather_batch(p(emb_all), p(gt_all), p(dist_all), p(idx), int(idx.numel()), n_rows,
+                                int(emb_all[0].numel()), p(emb_out), p(gt_out), p(dist_out), p(status),
+                                b._stream(gt_all.device))
     b.check(rc, "nvf_gather_batch")
 
 
@@ -50,8 +57,12 @@ def _loss_terms(net, emb, gt, dst, q, n_total, lmbda, w1, w2, focal_alpha, n_pts
         n_pts = D.allreduce_sum_(gt.sum())                       # batch-global (NVFPCC.py:154,161)
     out, cls_list, net_bits, latent_bits = net(emb, "train", q)
     bce, ms0, ms1, sums = ops.rd_distortion(out, cls_list[1], cls_list[0], gt, dst, focal_alpha, 0.85, 0.6)
-    # total loss + the logged scalars in one launch (forward) / one launch (backward)
-    loss, stats = ops.rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2)
+    # total loss + the logged scalars in one launch (forward) / one launch (backward).  Under data parallelism the
+    # ranks' weight gradients are SUMMED: the bce / ms / latent-rate terms are sums over the rank's own blocks, but
+    # the network-rate term lmbda*w2*sum(net_bits)/n_total is the same on every rank, so only rank 0 back-propagates it.
+    rank, _ = D.world()
+    loss, stats = ops.rd_total(sums, bce, ms0, ms1, latent_bits, net_bits, n_pts, n_total, lmbda, w1, w2,
+                               w2_grad=w2 if rank == 0 else 0.0)
     return loss, stats, sums
 
 
@@ -143,35 +154,57 @@ class WeightStep:
         self.dist = torch.zeros(batch, 1, 32, 32, 32, device=dev)
         self.stats = torch.zeros(len(STAT_NAMES), device=dev)
         self.sums = torch.zeros(ops._lib.NVF_LOSS_SUMS, dtype=torch.float64, device=dev)
+        self.n_pts = torch.zeros(1, device=dev)                  # batch-global point count handed in by the caller
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)   # sticky: bit 0 = a gather index was out of range
         self.use_graph = use_graph
         self.launches_per_step = 0
-        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.fused_opt = isinstance(opt, FusedAdam)
         if use_graph and not self.fused_opt:
             for g in opt.param_groups:
                 if not g.get("capturable", False):
                     raise ValueError("WeightStep(use_graph=True) needs FusedAdam or an optimizer built with capturable=True")
 
-    def _body(self, q: int):
+    def _body(self, q: int, ext_npts: bool = False):
+        """ext_npts: the batch-global point count was put into self.n_pts by the caller (known from the per-block
+        counts and the deterministic batch schedule: no reduction, no collective); otherwise it is gt.sum(),
+        all-reduced over the ranks (NVFPCC.py:154)."""
         self.opt.zero_grad(set_to_none=True)
-        loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q, **self.hp)
+        loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q,
+                                        n_pts=self.n_pts if ext_npts else None, **self.hp)
         loss.backward()
+        self._reduce_and_step()
+        self.stats.copy_(stats)
+        self.sums.copy_(sums)
+
+    def _reduce_and_step(self):
         if self.fused_opt:
             D.allreduce_sum_(self.opt.gather_grads())            # ONE all-reduce of the flat shared-weight gradient
             self.opt.step(gathered=True)
         else:
             D.allreduce_grads_(self.net.parameters())
             self.opt.step()
-        self.stats.copy_(stats)
-        self.sums.copy_(sums)
 
-    def _capture(self, q: int):
+    def empty_step(self) -> torch.Tensor:
+        """A step of a rank whose share of the minibatch is empty (short last batch of an epoch): it contributes a
+        zero gradient to the all-reduce and applies the same Adam update as the other ranks."""
+        if self.fused_opt:
+            for p in self.opt.ps:
+                p.grad = None
+        else:
+            for p in self.net.parameters():
+                p.grad = torch.zeros_like(p)
+        self._reduce_and_step()
+        self.stats.zero_()
+        return self.stats
+
+    def _capture(self, q: int, ext_npts: bool = False):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             state = self._snapshot()
             for _ in range(3):                                   # warm-up: allocator, lazy init, kernel attributes
-                self._body(q)
+                self._body(q, ext_npts)
             self._restore(state)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
@@ -179,10 +212,10 @@ class WeightStep:
         b = ops._lib.cuda_binding()
         n0 = b.launch_count()
         with torch.cuda.graph(g):
-            self._body(q)
+            self._body(q, ext_npts)
         self.launches_per_step = b.launch_count() - n0           # hand-written kernels inside one replay
         self._restore(state)                                     # capture does not run, but keep state exact
-        self._graphs[q] = g
+        self._graphs[(q, ext_npts)] = g
 
     def _snapshot(self):
         import copy
@@ -212,34 +245,51 @@ class WeightStep:
                         v.zero_()
 
     def step_indexed(self, emb_all: torch.Tensor, gt_all: torch.Tensor, dist_all: torch.Tensor, idx: torch.Tensor,
-                     q: int = 1) -> torch.Tensor:
+                     q: int = 1, n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
         """step() for device-resident float32 datasets: rows `idx` (int64, device) of the three tensors are gathered
         straight into the static buffers by ONE launch (nvf_gather_batch; advanced indexing + copy_ is six launches,
-        20 us per step; torch.index_select(out=) picks a 42 us small-index kernel)."""
-        ok = (gt_all.is_cuda and gt_all.dtype == torch.float32 and dist_all.dtype == torch.float32 and
-              emb_all.dtype == torch.float32 and gt_all.is_contiguous() and dist_all.is_contiguous() and
-              emb_all.is_contiguous() and idx.dtype == torch.int64 and idx.is_cuda and idx.numel() == self.emb.shape[0])
+        20 us per step; torch.index_select(out=) picks a 42 us small-index kernel).  n_pts: see step()."""
+        n_rows = int(gt_all.shape[0])
+        ok = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == n_rows
+                 for t in (emb_all, gt_all, dist_all))
+        ok = (ok and gt_all[0].numel() == 32768 and dist_all[0].numel() == 32768 and
+              emb_all[0].numel() == self.emb[0].numel() and idx.dtype == torch.int64 and idx.is_cuda and
+              idx.numel() == self.emb.shape[0] and idx.device == gt_all.device == self.emb.device)
         if not ok:
-            return self.step(emb_all.detach()[idx], gt_all[idx], dist_all[idx], q)
-        _gather_batch(emb_all.detach(), gt_all, dist_all, idx.contiguous(), self.emb, self.gt, self.dist)
-        return self._run(q)
+            idx_d = idx.to(emb_all.device)
+            return self.step(emb_all.detach()[idx_d], gt_all[idx.to(gt_all.device)], dist_all[idx.to(dist_all.device)],
+                             q, n_pts=n_pts)
+        _gather_batch(emb_all.detach(), gt_all, dist_all, idx.contiguous(), self.emb, self.gt, self.dist, self.status)
+        return self._run(q, n_pts)
 
-    def step(self, emb_batch: torch.Tensor, gt: torch.Tensor, dist_: torch.Tensor, q: int = 1) -> torch.Tensor:
+    def step(self, emb_batch: torch.Tensor, gt: torch.Tensor, dist_: torch.Tensor, q: int = 1,
+             n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """n_pts: optional 1-element tensor, the number of occupied voxels of the GLOBAL minibatch (NVFPCC.py:154);
+        when given, the step neither reduces gt nor all-reduces the scalar (the caller knows it from the per-block
+        counts of its dataset and the deterministic batch schedule, as trainer.fit does)."""
         self.emb.copy_(emb_batch.detach(), non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
         self.dist.copy_(dist_, non_blocking=True)
-        return self._run(q)
+        return self._run(q, n_pts)
 
-    def _run(self, q: int) -> torch.Tensor:
+    def _run(self, q: int, n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ext = n_pts is not None
+        if ext:
+            self.n_pts.copy_(n_pts.reshape(1), non_blocking=True)
         if not self.use_graph:
-            self._body(q)
+            self._body(q, ext)
             return self.stats
         if self.fused_opt:
             self.opt.sync_lr()
-        if q not in self._graphs:
-            self._capture(q)
-        self._graphs[q].replay()
+        if (q, ext) not in self._graphs:
+            self._capture(q, ext)
+        self._graphs[(q, ext)].replay()
         return self.stats
+
+    def check_status(self) -> None:
+        """Host read of the sticky status word (one synchronisation; call it when results are read anyway)."""
+        if int(self.status.item()) & 1:
+            raise ops.NvfError("nvf_gather_batch: a minibatch index was outside the dataset")
 
 
 class HostBatchFeeder:
@@ -351,6 +401,19 @@ def dataset_index(i: int, n_leaf: int, shuffle: bool = True) -> int:
     return (i * 2113) % n_leaf if shuffle else i
 
 
+def epoch_schedule(n_leaf_all: int, rank: int, world_size: int, batch_per_rank: int, shuffle: bool = True):
+    """Minibatch schedule of one epoch of the weight loop for `rank`: a list (one entry per step) of lists of
+    indices into the rank's OWN contiguous leaf range (dist.block_range).  Single process: exactly the batches of
+    DataLoader(dataset, batch_size, shuffle=False, drop_last=False) over LoadedVoxelDataset (NVFPCC.py:109-111,
+    utils/dataloader.py:163-167) - full batches, then one SHORT batch.  Every rank runs the step count of the
+    longest range; a rank whose range is exhausted gets empty batches at the end."""
+    lo, hi = D.block_range(n_leaf_all, rank, world_size)
+    n_leaf, B = hi - lo, int(batch_per_rank)
+    steps = (D.block_range(n_leaf_all, 0, world_size)[1] + B - 1) // B       # rank 0 holds the longest range
+    order = [dataset_index(i, n_leaf, shuffle) for i in range(n_leaf)]
+    return [order[s * B:min(n_leaf, (s + 1) * B)] for s in range(steps)]
+
+
 def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: int, lr: float, lmbda: float,
         w1: float = 1.0, w2: float = 1.0, wemb: float = 5.0, phase_change: int = 100, focal_alpha: float = 0.9,
         emb: Optional[torch.Tensor] = None, n_total: Optional[float] = None, start_epoch: int = 0,
@@ -360,8 +423,8 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
 
     gt / dist_: the whole dataset, [N_leaf,1,32,32,32] (uint8 / float, host or device) - kept resident
     in HBM (vox10: 1247 x 256 KB = 0.33 GB), so the weight loop has no H2D traffic.
-    Per epoch: the weight loop over all leaves at `batchsize` (drop_last=False; the short last batch
-    wraps around to keep the captured graph's shapes - it repeats leaves of the first batch), then ONE
+    Per epoch: the weight loop over all leaves at `batchsize` (drop_last=False: the last batch of an epoch is
+    short, exactly as the reference's DataLoader emits it; it runs through its own captured graph), then ONE
     full-batch embedding update, then both schedulers step on the WEIGHT optimizer (NVFPCC.py:126:
     sch_emb wraps `opt`, so the weight LR decays by 0.01 per milestone and the embedding LR never decays).
     Under torch.distributed each rank owns a contiguous range of leaves (embedding rows, gt/dist shards);
@@ -398,13 +461,24 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
     if batchsize % ws != 0:
         raise ValueError("batchsize must be a multiple of the number of ranks")
     B = batchsize // ws
-    wstep = WeightStep(net, opt, B, n_total, lmbda, w1, w2, focal_alpha, use_graph=use_graph, device=dev)
     estep = EmbeddingStep(net, emb_local, opt_emb, n_total, lmbda, w1, w2, focal_alpha)
-    steps = (n_leaf + B - 1) // B
-    if ws > 1:                                                                      # same step count on every rank
-        steps = (D.block_range(n_leaf_all, 0, ws)[1] + B - 1) // B                  # rank 0 holds the longest range
-    order = torch.tensor([dataset_index(i, n_leaf, dataset_shuffle) for i in range(n_leaf)], device=dev)
-    batches = [order[(torch.arange(B, device=dev) + s * B) % n_leaf].contiguous() for s in range(steps)]   # built once
+    # minibatch schedule of one epoch, built once.  DataLoader(drop_last=False) (NVFPCC.py:109-111): the last batch
+    # of an epoch is SHORT, not padded - a second step object (own static buffers + graph) handles its size.  Under
+    # torch.distributed every rank runs the step count of the longest range; a rank whose range is exhausted
+    # contributes a zero gradient (WeightStep.empty_step).
+    batches = [torch.tensor(b, dtype=torch.int64, device=dev)
+               for b in epoch_schedule(n_leaf_all, rank, ws, B, dataset_shuffle)]
+    steps = len(batches)
+    wsteps: Dict[int, WeightStep] = {}
+    for nb in sorted({int(b.numel()) for b in batches} | {B}, reverse=True):
+        if nb > 0:
+            wsteps[nb] = WeightStep(net, opt, nb, n_total, lmbda, w1, w2, focal_alpha, use_graph=use_graph, device=dev)
+    wstep = wsteps[B]
+    # batch-global n_pts of every step (NVFPCC.py:154) from the per-block point counts: one all-reduce of a
+    # `steps`-long vector at set-up instead of a reduction + a scalar all-reduce inside every step
+    cnt = gt_d.reshape(n_leaf, -1).sum(1)
+    npts_steps = torch.stack([cnt[b].sum() if b.numel() else cnt.new_zeros(()) for b in batches])
+    npts_steps = D.allreduce_sum_(npts_steps).reshape(steps, 1)
     history = []
     acc = torch.zeros(len(STAT_NAMES), device=dev)
     q = 1 if start_epoch < phase_change else 2
@@ -413,13 +487,18 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
             q = 2
         acc.zero_()
         for s in range(steps):
-            st = wstep.step_indexed(emb_local, gt_d, dist_d, batches[s], q=q)
-            acc += st
+            nb = int(batches[s].numel())
+            if nb == 0:
+                wstep.empty_step()
+                continue
+            acc += wsteps[nb].step_indexed(emb_local, gt_d, dist_d, batches[s], q=q, n_pts=npts_steps[s])
         est = estep.step(gt_d, dist_d, q)
         with warnings.catch_warnings():          # the graph replays opt.step(); the schedulers cannot see it
             warnings.simplefilter("ignore", UserWarning)
             sch_emb.step()
             sch.step()
+        for w_ in wsteps.values():
+            w_.check_status()
         rec = dict(zip(STAT_NAMES, (acc / steps).tolist()))                         # the epoch's only host read
         rec.update(epoch=epoch, q=q, emb_loss=float(est[0]), lr=float(opt.param_groups[0]["lr"]))
         history.append(rec)

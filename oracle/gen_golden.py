@@ -10,6 +10,9 @@ it the CUDA path) to the reference's own PyTorch modules:
   deltas), one weight-loop training step (NVFPCC.py:149-197) on 2 real
   synthetic leaf blocks incl. every parameter/embedding gradient.
 * nvf_B.npz  chanstr 16,32,16,16 ch=3: decode of 1 block.
+* nvf_train2.npz  two more weight-loop steps of the reference: config A at q=1
+  (the noisy-kernel phase the bench runs; the uniform noises the reference drew
+  are stored so the step can be replayed exactly) and config B at q=2.
 
 Inputs are rebuilt by `fixture_inputs()` from fixed seeds (shared with the
 tests); a checksum of the rebuilt state is stored so RNG drift is detected.
@@ -99,6 +102,62 @@ def fixture_inputs(tag):
     return dict(ch=ch, channels=channels, sd=sd, latents=latents, emb=emb, latent_noise=latent_noise)
 
 
+Q_LAYERS_FWD = ("up0", "conv0", "up1", "conv1", "up2", "conv2", "conv2_cls")   # torch.rand_like order at q=1
+
+
+def reference_train_step(net, RL, fx, gt, dist, q, seed, n_total=849338.0):
+    """One weight-loop step of train() (NVFPCC.py:149-197) on the reference modules -> dict of everything the
+    tests compare.  The RNG draws are replayed first so they can be stored: entropy_coder draws rand_like(latent)
+    (utils/network.py:4516), then at q=1 every Q-layer draws rand_like(kernel) in forward order (:610, :679)."""
+    gt_t, dist_t = torch.from_numpy(gt).float(), torch.from_numpy(dist).float()
+    emb = fx["emb"].clone().requires_grad_(True)
+    torch.manual_seed(seed)
+    noise_lat = torch.rand_like(emb)
+    noise_k = {}
+    if q == 1:
+        for name in Q_LAYERS_FWD:
+            noise_k[name] = torch.rand_like(getattr(net.reconstructor, name).kernel)
+    torch.manual_seed(seed)
+    net.train()
+    net.zero_grad()
+    out, out_cls, net_bits, latent_bits = net(emb, "train", q)
+    n_pts = gt_t.sum()
+    gts = O.gt_pyramid(gt_t)
+    bpp_loss = latent_bits.sum() / n_pts * TRAIN_HP["w1"] + net_bits.sum() / n_total * TRAIN_HP["w2"]
+    ms0 = RL.get_focal_dense(out_cls[0], gts[0], alpha=0.85)
+    ms1 = RL.get_focal_dense(out_cls[1], gts[1], alpha=0.85)
+    bce = RL.get_surf_focal_dense(out, gt_t, dist_t, beta=1, alpha=0.9)
+    loss = bce + ms0 + ms1 + TRAIN_HP["lmbda"] * bpp_loss
+    loss.backward()
+    r = dict(latent_noise=noise_lat.numpy(), out=out.detach().numpy(), cls0=out_cls[0].detach().numpy(),
+             cls1=out_cls[1].detach().numpy(), net_bits=net_bits.detach().numpy(),
+             latent_bits=np.float64(latent_bits.item()), loss=np.float64(loss.item()), bce=np.float64(bce.item()),
+             ms0=np.float64(ms0.item()), ms1=np.float64(ms1.item()), grad_emb=emb.grad.numpy())
+    for name, t in noise_k.items():
+        r["knoise::" + name] = t.numpy()
+    for k, p_ in net.named_parameters():
+        r["grad::" + k] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).numpy()
+    return r
+
+
+def gen_train2(RL):
+    save = {}
+    for tag, q, blocks, seed in (("A", 1, (0, 600), 777), ("B", 2, (300,), 778)):
+        fx = fixture_inputs(tag)
+        net = ref_import.build_net(fx["ch"], fx["channels"])
+        net.load_state_dict(fx["sd"], strict=True)
+        origins, gt, dist = fixture_blocks(blocks)
+        r = reference_train_step(net, RL, fx, gt, dist, q, seed)
+        pre = "%sq%d_" % (tag, q)
+        save[pre + "gt"] = gt
+        save[pre + "dist"] = dist.astype(np.float32)
+        for k, v in r.items():
+            save[pre + k] = v
+    path = os.path.join(GOLDEN, "nvf_train2.npz")
+    np.savez_compressed(path, **save)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def _load_into_reference(net, sd):
     missing = net.load_state_dict(sd, strict=True)
     return missing
@@ -108,6 +167,8 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     _, RL, _ = ref_import.load()
+    if "--train2-only" in sys.argv:
+        return gen_train2(RL)
     for tag in ("A", "B"):
         fx = fixture_inputs(tag)
         sd = fx["sd"]
@@ -176,6 +237,7 @@ def main():
         path = os.path.join(GOLDEN, "nvf_%s.npz" % tag)
         np.savez_compressed(path, **save)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    gen_train2(RL)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a GPU skips the `gpu` tier instead of failing in it."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_A():
     import numpy as np
@@ -31,5 +42,6 @@ def gpu():
     """The product binding on a CUDA device (the `-m gpu` tier)."""
     import torch
     from nvfpcc_b200 import _lib
-    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     return _lib.cuda_binding()

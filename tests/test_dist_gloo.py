@@ -79,6 +79,48 @@ def test_gather_points_reproduces_single_rank_order():
     assert all(_run(_gather_case).values())
 
 
+def _gather_ragged_case(rank, world):
+    """rank 1 holds nothing at all: the gather must not post zero-sized transfers or hang."""
+    if rank == 0:
+        coords = torch.arange(12, dtype=torch.int32).reshape(4, 3)
+        counts = torch.tensor([1, 3], dtype=torch.int32)
+    else:
+        coords = torch.zeros((0, 3), dtype=torch.int32)
+        counts = torch.zeros((0,), dtype=torch.int32)
+    c, k = D.gather_points(coords, counts, dst=0)
+    if rank != 0:
+        return c is None
+    return bool(torch.equal(c, coords) and torch.equal(k, counts))
+
+
+def test_gather_points_with_an_empty_rank():
+    assert all(_run(_gather_ragged_case).values())
+
+
+def test_epoch_schedule_is_the_dataloader_with_a_short_last_batch():
+    """trainer.epoch_schedule: single process = DataLoader(batch_size, drop_last=False) over the stride-2113
+    dataset order (utils/dataloader.py:163-167, NVFPCC.py:109-111); sharded = every leaf exactly once per epoch,
+    equal step counts, short / empty batches only at the end."""
+    from nvfpcc_b200 import trainer
+    n, B = 1247, 16
+    one = trainer.epoch_schedule(n, 0, 1, B)
+    flat = [i for b in one for i in b]
+    assert flat == [(i * 2113) % n for i in range(n)] and sorted(flat) == list(range(n))
+    assert [len(b) for b in one] == [16] * 77 + [15]
+    for world in (2, 3, 8):
+        per = B // world if B % world == 0 else 4
+        scheds = [trainer.epoch_schedule(n, r, world, per) for r in range(world)]
+        assert len({len(s) for s in scheds}) == 1
+        seen = []
+        for r, sch in enumerate(scheds):
+            lo, hi = D.block_range(n, r, world)
+            sizes = [len(b) for b in sch]
+            assert all(a >= b for a, b in zip(sizes, sizes[1:])) and sizes[0] == per
+            seen += [lo + i for b in sch for i in b]
+            assert all(0 <= i < hi - lo for b in sch for i in b)
+        assert sorted(seen) == list(range(n))
+
+
 def _grad_case(rank, world):
     torch.manual_seed(0)
     lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))

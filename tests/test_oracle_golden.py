@@ -78,3 +78,43 @@ def test_threshold_points_order():
     pts, counts = O.threshold_points(p, np.array([[32, 64, 96], [0, 0, 0]]), 0.65)
     assert counts.tolist() == [2, 1]
     assert pts.tolist() == [[32, 95, 127], [33, 66, 99], [5, 0, 0]]
+
+
+@pytest.fixture(scope="module")
+def golden_train2():
+    import os
+    from tests.conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "nvf_train2.npz"))
+
+
+@pytest.mark.parametrize("tag,q", [("A", 1), ("B", 2)])
+def test_train_step_q1_A_and_q2_B_match_reference(golden_train2, tag, q):
+    """The two extra reference steps (oracle/gen_golden.py gen_train2): config A in the noisy-kernel phase
+    (q=1, the phase bench.py runs) with the reference's own uniform draws replayed, and config B at q=2."""
+    g, pre = golden_train2, "%sq%d_" % (tag, q)
+    fx = fixture_inputs(tag)
+    sd = {k: v.clone().requires_grad_(not (k.endswith("_init") or k.endswith("pedestal"))) for k, v in fx["sd"].items()}
+    emb = fx["emb"].clone().requires_grad_(True)
+    gt, dist = torch.from_numpy(g[pre + "gt"]).float(), torch.from_numpy(g[pre + "dist"]).float()
+    noises = {n: torch.from_numpy(g[pre + "knoise::" + n]) for n in O.Q_KERNEL_LAYERS} if q == 1 else None
+    res = O.net_forward(emb, sd, "train", q, latent_noise=torch.from_numpy(g[pre + "latent_noise"]),
+                        kernel_noises=noises)
+    L = O.train_loss(res, gt, dist, n_pts=gt.sum(), n_total=849338.0, **TRAIN_HP)
+    L["loss"].backward()
+    np.testing.assert_allclose(res["out"].detach().numpy(), g[pre + "out"], rtol=0, atol=0)
+    np.testing.assert_allclose(res["net_bits"].detach().numpy(), g[pre + "net_bits"], rtol=1e-6)
+    for k in ("loss", "bce", "ms0", "ms1"):
+        assert L[k].item() == pytest.approx(float(g[pre + k]), rel=1e-6), k
+    np.testing.assert_allclose(emb.grad.numpy(), g[pre + "grad_emb"], rtol=1e-5, atol=1e-7)
+    n = 0
+    for key in g.files:
+        if not key.startswith(pre + "grad::"):
+            continue
+        name = key[len(pre + "grad::"):]
+        got = sd[name].grad
+        got = torch.zeros_like(sd[name]) if got is None else got
+        ref = g[key]
+        np.testing.assert_allclose(got.numpy(), ref, rtol=1e-4, atol=1e-5 * max(1e-6, float(np.abs(ref).max())),
+                                   err_msg=name)
+        n += 1
+    assert n == 28
