@@ -278,6 +278,7 @@ class TrainWorkload:
             import torch.distributed as dist
             dist.all_reduce(npts)
         self.npts = npts.reshape(-1, 1)
+        self.packed = [self.ws.pack_schedule(i, n) for i, n in zip(self.idx_dev, self.npts)]
         self.last_loss = None
 
     def batch_idx(self, i):
@@ -288,7 +289,8 @@ class TrainWorkload:
         """One weight-loop step (NVFPCC.py:149-223): batch -> static buffers -> fused fwd + loss + bwd +
         all-reduce + Adam (one CUDA-graph replay), inputs resident in HBM."""
         k = i % len(self.idx_dev)
-        st = self.ws.step_indexed(self.emb, self.gt_dev, self.dist_dev, self.idx_dev[k], q=1, n_pts=self.npts[k])
+        st = self.ws.step_indexed(self.emb, self.gt_dev, self.dist_dev, self.idx_dev[k], q=1, n_pts=self.npts[k],
+                                  packed=self.packed[k])
         self.last_loss = st[0]
         return st
 

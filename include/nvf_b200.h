@@ -163,8 +163,10 @@ int nvf_loss_seeds(const float* out, const float* cls1, const float* cls0, const
  *   flags: NVF_BWD_WGRAD compute weight grads (else skipped, NVFPCC.py:225-251
  *          discards them), NVF_BWD_DLATENT compute d_latent (NVFPCC.py:149-223
  *          discards it).  Weight-gradient buffers are OVERWRITTEN.
+ *          NVF_BWD_DLOGIT: g_out/g_cls1/g_cls0 are gradients w.r.t. the LOGITS of the
+ *          three heads (the sigmoid derivative is already folded in; all three required).
  */
-enum { NVF_BWD_WGRAD = 1, NVF_BWD_DLATENT = 2 };
+enum { NVF_BWD_WGRAD = 1, NVF_BWD_DLATENT = 2, NVF_BWD_DLOGIT = 4 };
 int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* latent, int64_t n_blocks,
                        const float* g_out, const float* g_cls1, const float* g_cls0, int flags,
                        const NvfWeightGrads* gw, float* g_latent, void* workspace, size_t workspace_bytes,
@@ -263,6 +265,44 @@ int nvf_rd_total_backward(const float* g_loss, const float* n_pts, float n_total
  */
 int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* step,
                   const float* lr, float beta1, float beta2, float eps, void* stream);
+
+/*
+ * One weight-loop step of train() as ONE call (NVFPCC.py:149-197 up to `loss.backward()`): latent head ->
+ * parameter transforms -> decoder forward -> rate-distortion loss -> backward of all of it, with the gradients
+ * of the RAW trainable tensors written to caller-chosen destinations (slices of one flat gradient buffer, so the
+ * all-reduce and nvf_adam_step follow without a gather).  It composes the entry points above behind one boundary
+ * and replaces what only exists between them in a framework: the minibatch gather (blocks read their dataset rows
+ * through `idx`), the noise tensors (drawn in-kernel: Philox4x32-10 keyed by `seed`, indexed by the device-resident
+ * `rng_counter`, which the call advances), the loss finalisation / total loss / cotangent kernels (last-CTA
+ * finalisation inside the loss kernel) and the packing of the effective kernels (written by the parameter kernel).
+ *   emb [n_rows, ch,2,2,2], gt / dist [n_rows,1,32,32,32]: the resident dataset when idx != NULL (idx [n] int64,
+ *   device; out-of-range -> row 0 + bit 0 of *status), else the batch itself (n_rows ignored).
+ *   flags: NVF_BWD_WGRAD -> g_latent / g_params are written (every pointer required);
+ *          NVF_BWD_DLATENT -> g_emb [n, ch,2,2,2] (batch order) is written.
+ *   noise_latent [n,ch,2,2,2] / noise_kernel (layout of nvf_param_prep): explicit U(0,1) draws (tests); NULL = in-kernel.
+ *   n_pts [1] device scalar (NVFPCC.py:154, batch-global); w2_grad: weight of the network-rate term in the backward
+ *   pass (w2 on one rank, 0 on the others under data parallelism).
+ *   stats [7] (loss bce ms0 ms1 b_latent b_net n_pts), sums [NVF_LOSS_SUMS] double.
+ */
+typedef struct NvfStepArgs {
+  NvfDesc desc;
+  int32_t n, q, flags, train_mode;
+  const float* emb; const float* gt; const float* dist; const int64_t* idx; int64_t n_rows; int32_t* status;
+  NvfLatentParams latent; NvfParamSet params;
+  NvfLatentGrads g_latent; NvfParamGrads g_params; float* g_emb;
+  const float* noise_latent; const float* noise_kernel;
+  uint64_t seed; uint64_t* rng_counter;
+  const float* n_pts;
+  float n_total, lmbda, w1, w2, w2_grad, alpha_main, alpha_aux, thh_metric, noise_scale;
+  float latent_beta_bound, latent_gamma_bound, latent_pedestal, igdn_beta_bound, igdn_gamma_bound, igdn_pedestal;
+  float* stats; double* sums;
+} NvfStepArgs;
+int nvf_train_step_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, size_t* bytes_out);
+/* workspace: nvf_train_step_workspace_bytes(), zero-filled ONCE by the caller before its first use (ticket words). */
+int nvf_train_step(const NvfStepArgs* args, void* workspace, size_t workspace_bytes, void* stream);
+/* U[0,1) values number first..first+n-1 of noise stream `stream_id` (1 latent, 2 kernel) at step `step`: the exact
+ * values the in-kernel generators use (tests: distribution, determinism, replay of a fused step). */
+int nvf_rng_uniform(uint64_t seed, uint64_t step, int stream_id, int64_t first, int64_t n, float* out, void* stream);
 
 /* FP32 FFMA throughput micro-benchmark (roofline denominator):
  * runs `iters` dependent-chain FFMA batches on every SM; returns the number of

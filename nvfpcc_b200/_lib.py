@@ -25,7 +25,7 @@ WEIGHT_FIELDS = (
     "up2_w", "up2_b", "conv2_w", "conv2_b", "cls2_w", "cls2_b", "cls1_w", "cls1_b", "cls0_w", "cls0_b",
 )
 NVF_MODE_DECODE, NVF_MODE_TRAIN = 0, 1
-NVF_BWD_WGRAD, NVF_BWD_DLATENT = 1, 2
+NVF_BWD_WGRAD, NVF_BWD_DLATENT, NVF_BWD_DLOGIT = 1, 2, 4
 NVF_LOSS_SUMS = 20
 NVF_LOSS_CHUNKS = 16   # CTAs per block of nvf_loss_seeds (workspace: 8 * NVF_LOSS_SUMS * (NVF_LOSS_CHUNKS * n + 1) bytes)
 EXPORTS = (
@@ -33,6 +33,7 @@ EXPORTS = (
     "nvf_decode", "nvf_emit_points", "nvf_train_forward", "nvf_loss_seeds", "nvf_train_backward",
     "nvf_ffma_microbench", "nvf_param_prep", "nvf_param_prep_backward",
     "nvf_latent_forward", "nvf_latent_backward", "nvf_rd_total", "nvf_rd_total_backward", "nvf_adam_step",
+    "nvf_train_step_workspace_bytes", "nvf_train_step", "nvf_rng_uniform",
 )
 LATENT_FIELDS = ("kernel", "kernel_init", "b", "b_init", "gdn_beta", "gdn_gamma", "sigma", "mu")   # NvfLatentParams
 LATENT_GRAD_FIELDS = ("kernel", "b", "gdn_beta", "gdn_gamma", "sigma", "mu")                         # NvfLatentGrads
@@ -83,6 +84,20 @@ class NvfLatentGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in LATENT_GRAD_FIELDS]
 
 
+class NvfStepArgs(C.Structure):
+    """include/nvf_b200.h NvfStepArgs (field order is the ABI)."""
+    _fields_ = ([("desc", NvfDesc)] + [(n, C.c_int32) for n in ("n", "q", "flags", "train_mode")] +
+                [("emb", C.c_void_p), ("gt", C.c_void_p), ("dist", C.c_void_p), ("idx", C.c_void_p),
+                 ("n_rows", C.c_int64), ("status", C.c_void_p),
+                 ("latent", NvfLatentParams), ("params", NvfParamSet), ("g_latent", NvfLatentGrads),
+                 ("g_params", NvfParamGrads), ("g_emb", C.c_void_p), ("noise_latent", C.c_void_p),
+                 ("noise_kernel", C.c_void_p), ("seed", C.c_uint64), ("rng_counter", C.c_void_p), ("n_pts", C.c_void_p)] +
+                [(n, C.c_float) for n in ("n_total", "lmbda", "w1", "w2", "w2_grad", "alpha_main", "alpha_aux", "thh_metric",
+                                          "noise_scale", "latent_beta_bound", "latent_gamma_bound", "latent_pedestal",
+                                          "igdn_beta_bound", "igdn_gamma_bound", "igdn_pedestal")] +
+                [("stats", C.c_void_p), ("sums", C.c_void_p)])
+
+
 class NvfError(RuntimeError):
     pass
 
@@ -131,6 +146,9 @@ class Binding:
         L.nvf_rd_total.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
         L.nvf_rd_total_backward.argtypes = [vp, vp, f32, f32, f32, f32, vp, vp, vp, vp]
         L.nvf_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, f32, f32, f32, vp]
+        L.nvf_train_step_workspace_bytes.argtypes = [C.POINTER(NvfDesc), C.c_int64, C.POINTER(C.c_size_t)]
+        L.nvf_train_step.argtypes = [C.POINTER(NvfStepArgs), vp, C.c_size_t, vp]
+        L.nvf_rng_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int64, C.c_int64, vp, vp]
         if L.nvf_abi_version() != 1:
             raise NvfError("ABI version mismatch in %s" % path)
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -440,6 +458,26 @@ class Binding:
                                     _ptr(step), _ptr(lr), float(beta1), float(beta2), float(eps),
                                     self._stream(param.device))
         self.check(rc, "nvf_adam_step")
+
+    # ---- fused weight-loop step -------------------------------------------------------------------
+    def train_step_workspace(self, desc: NvfDesc, n: int, dev: torch.device) -> torch.Tensor:
+        """Zero-filled workspace of nvf_train_step for n blocks (owned by the caller: its address is baked into
+        captured graphs; the ticket words inside must start at zero and are left at zero by every call)."""
+        out = C.c_size_t(0)
+        self.check(self.lib.nvf_train_step_workspace_bytes(C.byref(desc), int(n), C.byref(out)),
+                   "nvf_train_step_workspace_bytes")
+        return torch.zeros(int(out.value), dtype=torch.uint8, device=dev)
+
+    def train_step(self, args: "NvfStepArgs", ws: torch.Tensor, dev: torch.device) -> None:
+        rc = self.lib.nvf_train_step(C.byref(args), _ptr(ws), ws.numel(), self._stream(dev))
+        self.check(rc, "nvf_train_step")
+
+    def rng_uniform(self, seed: int, step: int, stream_id: int, first: int, n: int, dev) -> torch.Tensor:
+        out = torch.empty(int(n), dtype=torch.float32, device=dev)
+        rc = self.lib.nvf_rng_uniform(int(seed), int(step), int(stream_id), int(first), int(n), _ptr(out),
+                                      self._stream(out.device))
+        self.check(rc, "nvf_rng_uniform")
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.nvf_launch_count())

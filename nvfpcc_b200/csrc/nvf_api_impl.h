@@ -334,17 +334,21 @@ struct Api {
           *g3 = grad + s.a3 * n, *g4 = grad + s.a4 * n, *g5 = grad + s.a5 * n;
     float* tmp3 = (float*)(ws + W.off_tmp3);
     float* tmp1 = (float*)(ws + W.off_tmp1);
-    float* gl2 = (float*)(ws + W.off_gl2);
-    float* gl1 = (float*)(ws + W.off_gl1);
-    float* gl0 = (float*)(ws + W.off_gl0);
+    const float* gl2 = (const float*)(ws + W.off_gl2);
+    const float* gl1 = (const float*)(ws + W.off_gl1);
+    const float* gl0 = (const float*)(ws + W.off_gl0);
     l.set_partial((float*)(ws + W.off_partial), partial_floats(d, n));
     const bool wg = (flags & NVF_BWD_WGRAD) != 0;
-    // the heads' probabilities were kept by nvf_train_forward: dL/dlogit = dL/dp * p (1 - p)
     LayerParams p{};
-    {
+    if (flags & NVF_BWD_DLOGIT) {
+      // the caller's gradients are already w.r.t. the logits (the fused step's loss kernel folds the sigmoid in)
+      if (!g_out || !g_cls1 || !g_cls0) return NVF_ERR_INVALID_ARG;
+      gl2 = g_out; gl1 = g_cls1; gl0 = g_cls0;
+    } else {
+      // the heads' probabilities were kept by nvf_train_forward: dL/dlogit = dL/dp * p (1 - p)
       SigBwd3Params sp{{g_out, g_cls1, g_cls0},
                        {(const float*)(ws + W.off_p2), (const float*)(ws + W.off_p1), (const float*)(ws + W.off_p0)},
-                       {gl2, gl1, gl0},
+                       {(float*)(ws + W.off_gl2), (float*)(ws + W.off_gl1), (float*)(ws + W.off_gl0)},
                        {(int64_t)n * kVox, (int64_t)n * 4096, (int64_t)n * 512}};
       int64_t grid = ((int64_t)n * (kVox + 4096 + 512) + kThreads - 1) / kThreads;
       if (grid > 4096) grid = 4096;

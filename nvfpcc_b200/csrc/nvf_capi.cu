@@ -13,6 +13,7 @@
 #include "nvf_fast_stem.cuh"
 #include "nvf_fast_params.cuh"
 #include "nvf_fast_latent.cuh"
+#include "nvf_step.cuh"
 
 namespace nvf {
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches); shared with nvf_prep.cu
@@ -901,6 +902,261 @@ int nvf_ffma_microbench(int variant, int64_t iters, float* sink, double* flops_o
   nvf_launch(k_ffma, dim3(grid), dim3(kThreads), (size_t)(0), l.st, variant, (long long)iters, sink);
   l.post();
   if (flops_out) *flops_out = 2.0 * 256.0 * (double)iters * (double)grid * kThreads;
+  return l.rc;
+}
+
+}  // extern "C"
+
+
+// ------------------------------------------------------------------ fused weight-loop step
+namespace {
+
+// element counts of the 20 effective tensors in NvfWeights / NvfWeightGrads field order
+void eff_sizes(const NvfDesc& d, int64_t (&n)[20]) {
+  const int64_t v[20] = {(int64_t)d.ch * d.c0 * 125, d.c0, d.c0, (int64_t)d.c0 * d.c0, (int64_t)d.c0 * d.c1 * 125, d.c1,
+                         (int64_t)d.c1 * d.c2 * 125, d.c2, (int64_t)d.c2 * d.c2 * 64, d.c2, (int64_t)d.c2 * d.c3 * 125, d.c3,
+                         (int64_t)d.c3 * d.c3 * 64, d.c3, (int64_t)d.c3 * 27, 1, (int64_t)d.c2 * 27, 1, (int64_t)d.c1 * 27, 1};
+  for (int i = 0; i < 20; ++i) n[i] = v[i];
+}
+
+struct StepWs {
+  size_t off_train, off_eff, off_geff, off_latent, off_glatent, off_scal, off_param, off_latws, off_tickets, off_losspart, total;
+  int64_t eff_off[20], eff_total;
+  static StepWs make(const NvfDesc& d, int64_t n) {
+    StepWs L{};
+    int64_t sz[20];
+    eff_sizes(d, sz);
+    int64_t eo = 0;
+    for (int i = 0; i < 20; ++i) { L.eff_off[i] = eo; eo += (sz[i] + 3) / 4 * 4; }
+    L.eff_total = eo;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+    L.off_train = take(TrainWs::make(d, n).total);
+    L.off_eff = take(sizeof(float) * (size_t)eo);
+    L.off_geff = take(sizeof(float) * (size_t)eo);
+    L.off_latent = take(sizeof(float) * (size_t)n * d.ch * 8);
+    L.off_glatent = take(sizeof(float) * (size_t)n * d.ch * 8);
+    L.off_scal = take(sizeof(float) * 32);
+    L.off_param = take(NVF_PARAM_WS_BYTES);
+    L.off_latws = take(NVF_LATENT_WS_BYTES);
+    L.off_tickets = take(64);
+    L.off_losspart = take(sizeof(double) * NVF_LOSS_SUMS * (size_t)n * kLossChunks);
+    L.total = o;
+    return L;
+  }
+};
+
+template <class PtrT>
+void eff_pointers(float* base, const StepWs& W, PtrT& out) {
+  // NvfWeights / NvfWeightGrads are 20 consecutive pointers in field order
+  auto** slots = reinterpret_cast<float**>(&out);
+  for (int i = 0; i < 20; ++i) slots[i] = base + W.eff_off[i];
+}
+
+template <int CH>
+void launch_latent(DevLauncher& l, fast::LatentKParams& kp, bool bwd) {
+  int grid = (int)(((int64_t)kp.n * 8 + fast::kLatentThreads - 1) / fast::kLatentThreads);
+  if (grid > fast::kLatentMaxCtas) grid = fast::kLatentMaxCtas;
+  if (bwd) nvf_launch(fast::k_latent_bwd<CH>, dim3(grid), dim3(fast::kLatentThreads), (size_t)(0), l.st, kp);
+  else nvf_launch(fast::k_latent_fwd<CH>, dim3(grid), dim3(fast::kLatentThreads), (size_t)(0), l.st, kp);
+  l.post();
+}
+void launch_latent_ch(DevLauncher& l, int ch, fast::LatentKParams& kp, bool bwd) {
+  switch (ch) {
+    case 1: launch_latent<1>(l, kp, bwd); break;
+    case 2: launch_latent<2>(l, kp, bwd); break;
+    case 3: launch_latent<3>(l, kp, bwd); break;
+    default: launch_latent<4>(l, kp, bwd); break;
+  }
+}
+
+int train_step_impl(DevLauncher& l, const NvfStepArgs& a, void* workspace, size_t workspace_bytes) {
+  const NvfDesc& d = a.desc;
+  if (a.n <= 0 || a.n > (1 << 20) || a.q < 0 || a.q > 2 || !a.emb || !a.gt || !a.dist || !a.n_pts || !a.stats || !a.sums ||
+      !workspace)
+    return NVF_ERR_INVALID_ARG;
+  if (!generic_supported(d)) return NVF_ERR_UNSUPPORTED;
+  if (d.ch < 1 || d.ch > 4) return NVF_ERR_UNSUPPORTED;
+  if (a.idx && a.n_rows < 1) return NVF_ERR_INVALID_ARG;
+  const bool wg = (a.flags & NVF_BWD_WGRAD) != 0, demb = (a.flags & NVF_BWD_DLATENT) != 0;
+  if (demb && !a.g_emb) return NVF_ERR_INVALID_ARG;
+  const bool need_rng = (a.q == 1 && !a.noise_kernel) || (a.train_mode && !a.noise_latent && a.noise_scale != 0.f);
+  if (need_rng && !a.rng_counter) return NVF_ERR_INVALID_ARG;
+  const int n = a.n;
+  const StepWs W = StepWs::make(d, n);
+  if (workspace_bytes < W.total) return NVF_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  char* tws = ws + W.off_train;
+  const TrainWs T = TrainWs::make(d, n);
+  float* eff = (float*)(ws + W.off_eff);
+  float* geff = (float*)(ws + W.off_geff);
+  float* latent = (float*)(ws + W.off_latent);
+  float* g_latent = (float*)(ws + W.off_glatent);
+  float* scal = (float*)(ws + W.off_scal);       // [0] latent_bits, [1..7] net_bits, [8] g latent_bits, [9..15] g net_bits
+  unsigned int* tickets = (unsigned int*)(ws + W.off_tickets);
+  const unsigned long long* ctr = (const unsigned long long*)a.rng_counter;
+
+  NvfWeights w{};
+  NvfWeightGrads gw{}, effw{};
+  eff_pointers(eff, W, effw);
+  eff_pointers(geff, W, gw);
+  {
+    float* const* src = reinterpret_cast<float* const*>(&effw);
+    const float** dst = reinterpret_cast<const float**>(&w);
+    for (int i = 0; i < 20; ++i) dst[i] = src[i];
+  }
+
+  // ---- latent head on the auxiliary stream ...
+  fast::LatentKParams lk{};
+  lk.emb = a.emb; lk.noise = a.noise_latent;
+  lk.kernel = a.latent.kernel; lk.kernel_init = a.latent.kernel_init; lk.b = a.latent.b; lk.b_init = a.latent.b_init;
+  lk.beta = a.latent.gdn_beta; lk.gamma = a.latent.gdn_gamma; lk.sigma = a.latent.sigma; lk.mu = a.latent.mu;
+  if (!lk.kernel || !lk.kernel_init || !lk.b || !lk.b_init || !lk.beta || !lk.gamma || !lk.sigma || !lk.mu)
+    return NVF_ERR_INVALID_ARG;
+  lk.beta_bound = a.latent_beta_bound; lk.gamma_bound = a.latent_gamma_bound; lk.pedestal = a.latent_pedestal;
+  lk.noise_scale = a.noise_scale; lk.n = n; lk.train = a.train_mode ? 1 : 0;
+  lk.ticket = (unsigned int*)(ws + W.off_latws);
+  lk.partial = (double*)(ws + W.off_latws + 16);
+  lk.idx = (const long long*)a.idx; lk.n_rows = a.n_rows;
+  lk.seed = a.seed; lk.rng_ctr = (a.noise_latent || !a.train_mode) ? nullptr : ctr;
+  lk.latent = latent; lk.bits_out = scal;
+  l.side_begin();
+  launch_latent_ch(l, d.ch, lk, false);
+  l.side_end();
+
+  // ---- ... while the parameter kernel writes the effective tensors, their packed layouts and net_bits
+  fast::ParamPrepParams pp{};
+  int rc = fill_param_jobs(d, a.params, pp);
+  if (rc != NVF_OK) return rc;
+  {
+    float *ww[NVF_NUM_CONV], *bb[NVF_NUM_CONV];
+    eff_slots_w(effw, ww, bb);
+    const GenericPacked g = GenericPacked::make(d);
+    float* packed = (float*)(tws + T.off_packed);
+    const int64_t pf[NVF_NUM_CONV] = {g.up0, g.conv0, g.up1, g.conv1, g.up2, g.conv2, g.cls2, g.cls1, g.cls0};
+    const int64_t pd[NVF_NUM_CONV] = {g.d_up0, g.d_conv0, g.d_up1, g.d_conv1, g.d_up2, g.d_conv2, g.d_cls2, g.d_cls1, g.d_cls0};
+    const int A[NVF_NUM_CONV] = {d.ch, d.c0, d.c1, d.c2, d.c2, d.c3, 1, 1, 1};
+    const int B[NVF_NUM_CONV] = {d.c0, d.c1, d.c2, d.c2, d.c3, d.c3, d.c3, d.c2, d.c1};
+    const int K3[NVF_NUM_CONV] = {125, 125, 125, 64, 125, 64, 27, 27, 27};
+    const int CT[NVF_NUM_CONV] = {1, 1, 1, 0, 1, 0, 0, 0, 0};
+    for (int i = 0; i < NVF_NUM_CONV; ++i) {
+      fast::ParamJob& J = pp.job[i];
+      J.w_out = ww[i]; J.b_out = bb[i];
+      J.pk_fwd = packed + pf[i]; J.pk_dg = packed + pd[i];
+      J.A = A[i]; J.B = B[i]; J.K3 = K3[i]; J.convT = CT[i];
+    }
+  }
+  pp.beta_out = effw.igdn_beta; pp.gamma_out = effw.igdn_gamma;
+  pp.noise = a.noise_kernel; pp.q = a.q;
+  pp.seed = a.seed; pp.rng_ctr = ctr;
+  pp.partial = (float*)(ws + W.off_param); pp.net_bits = scal + 1;
+  pp.beta_bound = a.igdn_beta_bound; pp.gamma_bound = a.igdn_gamma_bound; pp.pedestal = a.igdn_pedestal;
+  pp.ticket = tickets;
+  nvf_launch(fast::k_param_prep<false>, dim3(pp.total_chunks + 1), dim3(256), (size_t)(0), l.st, pp);
+  l.post();
+  l.join();
+
+  // ---- decoder forward (probabilities of the three heads stay in the workspace)
+  float* p2 = (float*)(tws + T.off_p2);
+  float* p1 = (float*)(tws + T.off_p1);
+  float* p0 = (float*)(tws + T.off_p0);
+  Api<DevLauncher>::forward_layers(l, d, w, (const float*)(tws + T.off_packed), latent, n, (float*)(tws + T.off_stash), p2, p1, p0);
+
+  // ---- loss, metrics, dL/dlogit, total loss and scalar cotangents: one launch
+  const bool bwd = wg || demb;
+  fast::LossStepParams lp{};
+  lp.out = p2; lp.cls1 = p1; lp.cls0 = p0; lp.gt = a.gt; lp.dist = a.dist;
+  lp.idx = (const long long*)a.idx; lp.n_rows = a.n_rows; lp.status = a.status;
+  lp.gl2 = bwd ? (float*)(tws + T.off_gl2) : nullptr;
+  lp.gl1 = bwd ? (float*)(tws + T.off_gl1) : nullptr;
+  lp.gl0 = bwd ? (float*)(tws + T.off_gl0) : nullptr;
+  lp.partial = (double*)(ws + W.off_losspart); lp.ticket = tickets + 2;
+  lp.alpha_main = a.alpha_main; lp.alpha_aux = a.alpha_aux; lp.thh_metric = a.thh_metric; lp.n = n;
+  lp.latent_bits = scal; lp.net_bits = scal + 1; lp.n_pts = a.n_pts;
+  lp.n_total = a.n_total; lp.lmbda = a.lmbda; lp.w1 = a.w1; lp.w2 = a.w2; lp.w2_grad = a.w2_grad;
+  lp.sums = a.sums; lp.stats = a.stats; lp.g_scal = scal + 8;
+  nvf_launch(fast::k_loss_step, dim3(n * kLossChunks), dim3(256), (size_t)(0), l.st, lp);
+  l.post();
+  if (!bwd) return l.rc;
+
+  // ---- decoder backward
+  rc = Api<DevLauncher>::train_backward(l, &d, &w, latent, n, lp.gl2, lp.gl1, lp.gl0,
+                                        (wg ? NVF_BWD_WGRAD : 0) | NVF_BWD_DLATENT | NVF_BWD_DLOGIT, wg ? &gw : nullptr,
+                                        g_latent, tws, T.total);
+  if (rc != NVF_OK) return rc;
+
+  // ---- latent head backward on the auxiliary stream, parameter-side backward on the caller's
+  lk.g_latent = g_latent; lk.g_bits = scal + 8; lk.g_emb = demb ? a.g_emb : nullptr;
+  if (wg) {
+    const NvfLatentGrads& G = a.g_latent;
+    if (!G.kernel || !G.b || !G.gdn_beta || !G.gdn_gamma || !G.sigma || !G.mu) return NVF_ERR_INVALID_ARG;
+    lk.gk = G.kernel; lk.gb = G.b; lk.gbeta = G.gdn_beta; lk.ggamma = G.gdn_gamma; lk.gsigma = G.sigma; lk.gmu = G.mu;
+  }
+  l.side_begin();
+  launch_latent_ch(l, d.ch, lk, true);
+  if (need_rng) {
+    nvf_launch(fast::k_rng_tick, dim3(1), dim3(1), (size_t)(0), l.st, (unsigned long long*)a.rng_counter);
+    l.post();
+  }
+  l.side_end();
+  if (wg) {
+    const NvfParamGrads& O = a.g_params;
+    const float* const* gwp = reinterpret_cast<const float* const*>(&gw);
+    // field order of NvfWeightGrads: up0_w up0_b igdn_beta igdn_gamma conv0_w conv0_b up1_w ... cls0_w cls0_b
+    const int wi[NVF_NUM_CONV] = {0, 4, 6, 8, 10, 12, 14, 16, 18};
+    for (int i = 0; i < NVF_NUM_CONV; ++i) {
+      if (!O.kernel[i] || !O.b[i]) return NVF_ERR_INVALID_ARG;
+      fast::ParamJob& J = pp.job[i];
+      J.g_w = gwp[wi[i]]; J.g_b = gwp[wi[i] + 1];
+      J.w_out = O.kernel[i]; J.b_out = O.b[i];
+      J.pk_fwd = nullptr; J.pk_dg = nullptr;
+    }
+    if (!O.igdn_beta || !O.igdn_gamma || !O.lik_sigma || !O.lik_mu) return NVF_ERR_INVALID_ARG;
+    pp.g_beta = gw.igdn_beta; pp.g_gamma = gw.igdn_gamma;
+    pp.beta_out = O.igdn_beta; pp.gamma_out = O.igdn_gamma;
+    pp.g_bits = scal + 9;
+    pp.g_sigma = O.lik_sigma; pp.g_mu = O.lik_mu;
+    pp.ticket = tickets + 1;
+    nvf_launch(fast::k_param_prep<true>, dim3(pp.total_chunks + 1), dim3(256), (size_t)(0), l.st, pp);
+    l.post();
+  }
+  l.join();
+  return l.rc;
+}
+
+__global__ void __launch_bounds__(256) k_rng_uniform(unsigned long long seed, unsigned long long step, unsigned int stream,
+                                                     long long first, long long n, float* out) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = rng::uniform(seed, step, stream, (uint64_t)(first + i));
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvf_train_step_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, size_t* bytes_out) {
+  if (!desc || !bytes_out || n_blocks < 0) return NVF_ERR_INVALID_ARG;
+  if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
+  *bytes_out = StepWs::make(*desc, n_blocks).total;
+  return NVF_OK;
+}
+
+int nvf_train_step(const NvfStepArgs* args, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!args) return NVF_ERR_INVALID_ARG;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  return train_step_impl(l, *args, workspace, workspace_bytes);
+}
+
+int nvf_rng_uniform(uint64_t seed, uint64_t step, int stream_id, int64_t first, int64_t n, float* out, void* stream) {
+  if (!out || n < 0 || first < 0 || stream_id < 0 || stream_id > 255) return NVF_ERR_INVALID_ARG;
+  if (n == 0) return NVF_OK;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  nvf_launch(k_rng_uniform, dim3(grid), dim3(256), (size_t)(0), l.st, (unsigned long long)seed, (unsigned long long)step,
+             (unsigned int)stream_id, (long long)first, (long long)n, out);
+  l.post();
   return l.rc;
 }
 

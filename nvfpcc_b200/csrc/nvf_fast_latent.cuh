@@ -42,6 +42,11 @@ struct LatentKParams {
   // scratch
   double* partial;                                  // [gridDim][NP]
   unsigned int* ticket;                             // zero on entry, zero on exit
+  // fused-step extras (all optional): block b reads embedding row idx[b] of a resident dataset with n_rows rows
+  // (out-of-range rows are clamped to 0 and reported by the caller's gather status); noise == null && rng_ctr:
+  // in-kernel Philox noise; g_bits_scale != null: g_bits[0] is multiplied by it (lambda * w1, the caller passes 1/n_pts)
+  const long long* idx; long long n_rows;
+  unsigned long long seed; const unsigned long long* rng_ctr;
 };
 
 template <int CH>
@@ -62,21 +67,6 @@ __device__ __forceinline__ double cta_sum_d(double v, double* sm) {
   return s;
 }
 
-// true on every thread of the LAST CTA to arrive (after its partials are visible)
-__device__ __forceinline__ bool last_cta(unsigned int* ticket) {
-  __shared__ unsigned int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) *ticket = 0u;
-  }
-  __syncthreads();
-  if (s_last) __threadfence();
-  return s_last != 0u;
-}
-
 template <int CH>
 struct LatentPoint {
   float e[CH], h[CH], nrm[CH], y[CH], r[CH], xt[CH];
@@ -90,8 +80,14 @@ __device__ __forceinline__ void latent_point(const LatentKParams& p, const float
   q.valid = pos < p.n * 8;
   const int blk = q.valid ? pos >> 3 : 0, s = pos & 7;
   const size_t base = (size_t)blk * CH * 8 + s;
+  size_t ebase = base;
+  if (p.idx) {
+    long long row = p.idx[blk];
+    if (row < 0 || row >= p.n_rows) row = 0;
+    ebase = (size_t)row * CH * 8 + s;
+  }
 #pragma unroll
-  for (int j = 0; j < CH; ++j) q.e[j] = q.valid ? p.emb[base + j * 8] : 0.f;
+  for (int j = 0; j < CH; ++j) q.e[j] = q.valid ? p.emb[ebase + j * 8] : 0.f;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     float v = bias[i];
@@ -109,6 +105,8 @@ __device__ __forceinline__ void latent_point(const LatentKParams& p, const float
     q.r[i] = rintf(q.y[i]);
     float nz = 0.f;
     if (p.noise && q.valid) nz = (p.noise[base + i * 8] - 0.5f) * p.noise_scale;
+    else if (p.rng_ctr && q.valid && p.train)
+      nz = (rng::uniform(p.seed, p.rng_ctr[0], rng::kLatentNoise, (uint64_t)(base + i * 8)) - 0.5f) * p.noise_scale;
     q.xt[i] = p.train ? q.y[i] + nz : q.r[i];
   }
 }

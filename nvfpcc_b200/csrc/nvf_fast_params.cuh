@@ -9,9 +9,26 @@
 #include <cuda_runtime.h>
 #include "../../include/nvf_b200.h"
 #include "nvf_common.h"
+#include "nvf_rng.cuh"
 
 namespace nvf {
 namespace fast {
+
+// true on every thread of the LAST CTA of the grid to arrive (after its global writes are visible);
+// the ticket word is zero on entry and left zero.
+__device__ __forceinline__ bool last_cta(unsigned int* ticket) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1) ? 1u : 0u;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
+}
 
 constexpr int kParamChunk = 1024;   // elements per CTA (256 threads x 4)
 constexpr int kNumConv = 9;         // up0 conv0 up1 conv1 up2 conv2 conv2_cls | conv1_cls conv0_cls
@@ -22,6 +39,9 @@ struct ParamJob {
   float* w_out; float* b_out;               // forward: effective tensors   | backward: gradient outputs
   const float* g_w; const float* g_b;       // backward: gradients w.r.t. the effective tensors
   int32_t n, nb, chunk0, nchunks, noise0;
+  // optional: the packed layouts the conv kernels read (nvf_common.h PackMode), written in the same pass
+  float* pk_fwd; float* pk_dg;              // dst[ci][k][co] and dst[co][k (flipped for conv)][ci], or null
+  int32_t A, B, K3, convT;                  // source dims: convT (A=Ci,B=Co,K^3) | conv (A=Co,B=Ci,K^3)
 };
 struct ParamPrepParams {
   ParamJob job[kNumConv];
@@ -36,7 +56,28 @@ struct ParamPrepParams {
   float* g_sigma; float* g_mu;                         // backward final
   float beta_bound, gamma_bound, pedestal;
   int32_t q, c0, total_chunks;
+  // fused-step extras: in-kernel noise (noise == null, rng_ctr != null), finalisation by the last CTA (ticket != null)
+  unsigned long long seed; const unsigned long long* rng_ctr;
+  unsigned int* ticket;
 };
+
+// net_bits (forward) / d sigma, d mu (backward) from the per-chunk partials, in chunk order (deterministic)
+template <bool BWD>
+__device__ __forceinline__ void param_finalise(const ParamPrepParams& p, int l) {
+  if (!BWD) {
+    if (l < kNumQuant) {
+      float s = 0.f;
+      for (int c = 0; c < p.job[l].nchunks; ++c) s += p.partial[(p.job[l].chunk0 + c) * 3];
+      p.net_bits[l] = s;
+    }
+  } else if (l < 2) {
+    float s = 0.f;
+    for (int j = 0; j < kNumQuant; ++j)
+      for (int c = 0; c < p.job[j].nchunks; ++c) s += p.partial[(p.job[j].chunk0 + c) * 3 + 1 + l];
+    if (l == 0) p.g_sigma[0] = p.lik_sigma[0] > 0.f ? s : (p.lik_sigma[0] < 0.f ? -s : 0.f);
+    else p.g_mu[0] = s;
+  }
+}
 
 __device__ __forceinline__ float phi_cdf(float x) { return 0.5f * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float phi_pdf(float x) { return 0.39894228040143267794f * expf(-0.5f * x * x); }
@@ -78,6 +119,7 @@ __global__ void __launch_bounds__(256) k_param_prep(ParamPrepParams p) {
         *out = (raw >= bound || g < 0.f) ? g : 0.f;
       }
     }
+    if (p.ticket && last_cta(p.ticket)) param_finalise<BWD>(p, tid);
     return;
   }
   int l = 0;
@@ -99,9 +141,22 @@ __global__ void __launch_bounds__(256) k_param_prep(ParamPrepParams p) {
     const float r = rintf(kv * 16.f) / 16.f;
     if (!BWD) {
       float kq = kv;
-      if (quant && p.q == 1) kq = kv + (p.noise[J.noise0 + i] - 0.5f) * (1.f / 16.f);
-      else if (quant && p.q == 2) kq = r;
-      J.w_out[i] = kq + J.init[i];
+      if (quant && p.q == 1) {
+        const float u01 = p.noise ? p.noise[J.noise0 + i]
+                                  : rng::uniform(p.seed, p.rng_ctr[0], rng::kKernelNoise, (uint64_t)(J.noise0 + i));
+        kq = kv + (u01 - 0.5f) * (1.f / 16.f);
+      } else if (quant && p.q == 2) {
+        kq = r;
+      }
+      const float we = kq + J.init[i];
+      J.w_out[i] = we;
+      if (J.pk_fwd) {
+        // source index i = (a * B + b) * K3 + k
+        const int k = i % J.K3, ab = i / J.K3, bb = ab % J.B, aa = ab / J.B;
+        const int ci = J.convT ? aa : bb, co = J.convT ? bb : aa, Ci = J.convT ? J.A : J.B, Co = J.convT ? J.B : J.A;
+        J.pk_fwd[(ci * J.K3 + k) * Co + co] = we;
+        if (J.pk_dg) J.pk_dg[(co * J.K3 + (J.convT ? k : J.K3 - 1 - k)) * Ci + ci] = we;
+      }
       if (quant) {
         const float u = (r - mu + h) / sigma, lo = (r - mu - h) / sigma;
         const float L = fmaxf(phi_cdf(u) - phi_cdf(lo), 1e-8f);
@@ -134,25 +189,13 @@ __global__ void __launch_bounds__(256) k_param_prep(ParamPrepParams p) {
       if (tid == 0) { p.partial[blockIdx.x * 3 + 1] = a; p.partial[blockIdx.x * 3 + 2] = b; }
     }
   }
+  if (p.ticket && last_cta(p.ticket)) param_finalise<BWD>(p, tid);
 }
 
 template <bool BWD>
 __global__ void __launch_bounds__(32) k_param_final(ParamPrepParams p) {
   pdl_entry();
-  const int l = threadIdx.x;
-  if (!BWD) {
-    if (l < kNumQuant) {
-      float s = 0.f;
-      for (int c = 0; c < p.job[l].nchunks; ++c) s += p.partial[(p.job[l].chunk0 + c) * 3];
-      p.net_bits[l] = s;
-    }
-  } else if (l < 2) {
-    float s = 0.f;
-    for (int j = 0; j < kNumQuant; ++j)
-      for (int c = 0; c < p.job[j].nchunks; ++c) s += p.partial[(p.job[j].chunk0 + c) * 3 + 1 + l];
-    if (l == 0) p.g_sigma[0] = p.lik_sigma[0] > 0.f ? s : (p.lik_sigma[0] < 0.f ? -s : 0.f);
-    else p.g_mu[0] = s;
-  }
+  param_finalise<BWD>(p, (int)threadIdx.x);
 }
 
 }  // namespace fast

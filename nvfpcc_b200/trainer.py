@@ -135,6 +135,102 @@ class FusedAdam(torch.optim.Optimizer):
             t.copy_(s)
 
 
+class FusedStepCall:
+    """Argument block of nvf_train_step for one (net, batch size) pair: raw-parameter pointers, gradient destinations
+    (slices of FusedAdam.flat_grad when an optimizer is given, else private buffers), the step's workspace and the
+    device-resident noise counter.  Built once; `run()` is one C call (about 45 kernel launches, no framework op)."""
+
+    def __init__(self, net, n: int, n_total: float, lmbda: float, w1: float, w2: float, focal_alpha: float,
+                 opt: Optional["FusedAdam"], dev, want_wgrad: bool = True, want_demb: bool = False, seed: int = 0):
+        import ctypes as C
+        L = ops._lib
+        self.b = L.cuda_binding()
+        self.net, self.dev, self.n = net, dev, int(n)
+        rec = net.reconstructor
+        ch = rec.in_channels
+        if ch > 4:
+            raise ops.NvfError("the fused step supports ch <= 4")
+        self.desc = self.b.desc(ch, rec.channels)
+        self.ws = self.b.train_step_workspace(self.desc, n, dev)
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.g_emb = torch.zeros(n, ch, 2, 2, 2, device=dev) if want_demb else None
+        a = L.NvfStepArgs()
+        a.desc, a.n = self.desc, int(n)
+        a.flags = (L.NVF_BWD_WGRAD if want_wgrad else 0) | (L.NVF_BWD_DLATENT if want_demb else 0)
+        self._keep = []
+
+        def ptr(t):
+            if not t.is_cuda or (torch.device(dev).index not in (None, t.device.index)):
+                raise ops.NvfError("fused step: every tensor must live on %s" % (dev,))
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ops.NvfError("fused step: float32 contiguous tensors required")
+            self._keep.append(t)
+            return t.data_ptr()
+
+        # gradient destinations: views of the optimizer's flat gradient buffer (no gather before the all-reduce / Adam)
+        if want_wgrad:
+            if opt is not None:
+                off, o = {}, 0
+                for p_ in opt.ps:
+                    off[id(p_)] = o
+                    o += p_.numel()
+                gdst = lambda p_: opt.flat_grad[off[id(p_)]:off[id(p_)] + p_.numel()]
+            else:
+                self.grads = {}
+                def gdst(p_):
+                    g = torch.zeros(p_.numel(), device=dev)
+                    self.grads[id(p_)] = g
+                    return g
+        raw = rec.raw_tensors()
+        for i, name in enumerate(L.CONV_LAYERS):
+            for field in ("kernel", "kernel_init", "b", "b_init"):
+                getattr(a.params, field)[i] = ptr(raw["%s_%s" % (name, field)].detach())
+            if want_wgrad:
+                a.g_params.kernel[i] = ptr(gdst(raw[name + "_kernel"]))
+                a.g_params.b[i] = ptr(gdst(raw[name + "_b"]))
+        for field in ("igdn_beta", "igdn_gamma", "lik_sigma", "lik_mu"):
+            setattr(a.params, field, ptr(raw[field].detach()))
+            if want_wgrad:
+                setattr(a.g_params, field, ptr(gdst(raw[field])))
+        lraw = net.latent_raw()
+        for field in L.LATENT_FIELDS:
+            setattr(a.latent, field, ptr(lraw[field].detach()))
+        if want_wgrad:
+            for field in L.LATENT_GRAD_FIELDS:
+                setattr(a.g_latent, field, ptr(gdst(lraw[field])))
+        if want_demb:
+            a.g_emb = ptr(self.g_emb)
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.rng_counter = self.rng_counter.data_ptr()
+        a.n_total, a.lmbda, a.w1, a.w2 = float(n_total), float(lmbda), float(w1), float(w2)
+        a.alpha_main, a.alpha_aux, a.thh_metric = float(focal_alpha), 0.85, 0.6
+        g, act = net.latent_gen.gdn_2, rec.activation
+        a.latent_beta_bound, a.latent_gamma_bound, a.latent_pedestal = (float(g.beta_bound), float(g.gamma_bound),
+                                                                         float(g.reparam_pedestal))
+        a.igdn_beta_bound, a.igdn_gamma_bound, a.igdn_pedestal = (float(act.beta_bound), float(act.gamma_bound),
+                                                                  float(act.reparam_pedestal))
+        self.args = a
+
+    def run(self, emb, gt, dist_, idx, n_rows, n_pts, stats, sums, q: int, mode: str = "train", status=None,
+            noise_latent=None, noise_kernel=None):
+        """emb / gt / dist_: the batch (idx None) or the resident dataset with rows idx (int64, device)."""
+        a = self.args
+        p = ops._lib._ptr
+        a.q, a.train_mode = int(q), 1 if mode == "train" else 0
+        a.emb, a.gt, a.dist = emb.data_ptr(), gt.data_ptr(), dist_.data_ptr()
+        a.idx = None if idx is None else idx.data_ptr()
+        a.n_rows = int(n_rows)
+        a.status = None if status is None else status.data_ptr()
+        a.n_pts = n_pts.data_ptr()
+        a.noise_scale = float(self.net.entropy_coder.noise_scale)
+        rank, _ = D.world()
+        a.w2_grad = a.w2 if rank == 0 else 0.0
+        a.noise_latent = None if noise_latent is None else noise_latent.data_ptr()
+        a.noise_kernel = None if noise_kernel is None else noise_kernel.data_ptr()
+        a.stats, a.sums = stats.data_ptr(), sums.data_ptr()
+        self.b.train_step(a, self.ws, self.dev)
+
+
 class WeightStep:
     """One minibatch update of the shared decoder weights (NVFPCC.py:149-223).
 
@@ -143,7 +239,13 @@ class WeightStep:
     the device-resident stats tensor (see STAT_NAMES) - no host synchronisation."""
 
     def __init__(self, net, opt: torch.optim.Optimizer, batch: int, n_total: float, lmbda: float, w1: float,
-                 w2: float, focal_alpha: float = 0.9, use_graph: bool = True, device=None):
+                 w2: float, focal_alpha: float = 0.9, use_graph: bool = True, device=None, fused: Optional[bool] = None,
+                 seed: Optional[int] = None):
+        """fused: run the step through nvf_train_step (one C call: in-kernel gather and noise, one-launch loss,
+        gradients written straight into the flat buffer) instead of the autograd graph over the individual ops.
+        Default: on whenever the optimizer is a FusedAdam.  Same kernels for the heavy layers, same results up to
+        summation order; the noise of the q = 1 / train phases comes from the in-kernel Philox streams (seeded by
+        `seed`, default torch.initial_seed()) instead of torch.rand."""
         self.net, self.opt = net, opt
         self.hp = dict(n_total=float(n_total), lmbda=float(lmbda), w1=float(w1), w2=float(w2),
                        focal_alpha=float(focal_alpha))
@@ -154,21 +256,34 @@ class WeightStep:
         self.dist = torch.zeros(batch, 1, 32, 32, 32, device=dev)
         self.stats = torch.zeros(len(STAT_NAMES), device=dev)
         self.sums = torch.zeros(ops._lib.NVF_LOSS_SUMS, dtype=torch.float64, device=dev)
-        self.n_pts = torch.zeros(1, device=dev)                  # batch-global point count handed in by the caller
+        # [0:batch] minibatch row indices, [batch] the batch-global point count (float32 bits in the low half): one
+        # small buffer so that a precomputed schedule row (pack_schedule) reaches the step with ONE async copy
+        self._hdr = torch.zeros(batch + 1, dtype=torch.int64, device=dev)
+        self._idx_buf = self._hdr[:batch]
+        self.n_pts = self._hdr[batch:].view(torch.float32)[:1]   # batch-global point count handed in by the caller
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)   # sticky: bit 0 = a gather index was out of range
         self.use_graph = use_graph
         self.launches_per_step = 0
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.fused_opt = isinstance(opt, FusedAdam)
+        self.fused = self.fused_opt and net.reconstructor.in_channels <= 4 if fused is None else bool(fused)
+        if self.fused and not self.fused_opt:
+            raise ValueError("WeightStep(fused=True) needs a FusedAdam optimizer (gradients go to its flat buffer)")
+        self._call = None
+        self._idx_src = None           # (emb_all, gt_all, dist_all) of the pending step_indexed call
+        self._seed = int(torch.initial_seed() if seed is None else seed)
         if use_graph and not self.fused_opt:
             for g in opt.param_groups:
                 if not g.get("capturable", False):
                     raise ValueError("WeightStep(use_graph=True) needs FusedAdam or an optimizer built with capturable=True")
 
-    def _body(self, q: int, ext_npts: bool = False):
+    def _body(self, q: int, ext_npts: bool = False, indexed: bool = False):
         """ext_npts: the batch-global point count was put into self.n_pts by the caller (known from the per-block
         counts and the deterministic batch schedule: no reduction, no collective); otherwise it is gt.sum(),
-        all-reduced over the ranks (NVFPCC.py:154)."""
+        all-reduced over the ranks (NVFPCC.py:154).  indexed (fused path only): the blocks read rows self._idx_buf
+        of the resident dataset self._idx_src directly - no gather."""
+        if self.fused:
+            return self._body_fused(q, ext_npts, indexed)
         self.opt.zero_grad(set_to_none=True)
         loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q,
                                         n_pts=self.n_pts if ext_npts else None, **self.hp)
@@ -176,6 +291,22 @@ class WeightStep:
         self._reduce_and_step()
         self.stats.copy_(stats)
         self.sums.copy_(sums)
+
+    def _body_fused(self, q: int, ext_npts: bool, indexed: bool = False):
+        if self._call is None:
+            hp = self.hp
+            self._call = FusedStepCall(self.net, self.emb.shape[0], hp["n_total"], hp["lmbda"], hp["w1"], hp["w2"],
+                                       hp["focal_alpha"], self.opt, self.emb.device, seed=self._seed)
+        if not ext_npts:
+            self.n_pts.copy_(D.allreduce_sum_(self.gt.sum()).reshape(1))      # batch-global (NVFPCC.py:154,161)
+        if indexed:
+            emb_all, gt_all, dist_all = self._idx_src
+            self._call.run(emb_all, gt_all, dist_all, self._idx_buf, gt_all.shape[0], self.n_pts, self.stats, self.sums,
+                           q, status=self.status)
+        else:
+            self._call.run(self.emb, self.gt, self.dist, None, 0, self.n_pts, self.stats, self.sums, q)
+        D.allreduce_sum_(self.opt.flat_grad)                                  # ONE all-reduce, in place
+        self.opt.step(gathered=True)
 
     def _reduce_and_step(self):
         if self.fused_opt:
@@ -198,13 +329,13 @@ class WeightStep:
         self.stats.zero_()
         return self.stats
 
-    def _capture(self, q: int, ext_npts: bool = False):
+    def _capture(self, key, q: int, ext_npts: bool = False, indexed: bool = False):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             state = self._snapshot()
             for _ in range(3):                                   # warm-up: allocator, lazy init, kernel attributes
-                self._body(q, ext_npts)
+                self._body(q, ext_npts, indexed)
             self._restore(state)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
@@ -212,21 +343,24 @@ class WeightStep:
         b = ops._lib.cuda_binding()
         n0 = b.launch_count()
         with torch.cuda.graph(g):
-            self._body(q, ext_npts)
+            self._body(q, ext_npts, indexed)
         self.launches_per_step = b.launch_count() - n0           # hand-written kernels inside one replay
         self._restore(state)                                     # capture does not run, but keep state exact
-        self._graphs[(q, ext_npts)] = g
+        self._graphs[key] = g
 
     def _snapshot(self):
         import copy
         if self.fused_opt:
-            return self.opt.snapshot()
+            extra = [self._call.rng_counter.clone()] if self._call is not None else []
+            return self.opt.snapshot() + extra
         return [p.detach().clone() for p in self.net.parameters()], copy.deepcopy(self.opt.state_dict())
 
     def _restore(self, state):
         if self.fused_opt:
             with torch.no_grad():
-                self.opt.restore(state)
+                self.opt.restore(state[:4])
+                if len(state) > 4 and self._call is not None:
+                    self._call.rng_counter.copy_(state[4])
             return
         params, opt_sd = state
         with torch.no_grad():
@@ -244,11 +378,20 @@ class WeightStep:
                     if torch.is_tensor(v):
                         v.zero_()
 
+    def pack_schedule(self, idx: torch.Tensor, n_pts: torch.Tensor) -> torch.Tensor:
+        """One schedule row for step_indexed(packed=...): the minibatch indices and the batch-global point count in
+        the layout of the step's header buffer (built once per run by trainer.fit / bench.py)."""
+        row = torch.zeros(self._hdr.shape[0], dtype=torch.int64, device=self._hdr.device)
+        row[:-1] = idx.to(row.device)
+        row[-1:].view(torch.float32)[0] = n_pts.reshape(()).to(row.device, torch.float32)
+        return row
+
     def step_indexed(self, emb_all: torch.Tensor, gt_all: torch.Tensor, dist_all: torch.Tensor, idx: torch.Tensor,
-                     q: int = 1, n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """step() for device-resident float32 datasets: rows `idx` (int64, device) of the three tensors are gathered
-        straight into the static buffers by ONE launch (nvf_gather_batch; advanced indexing + copy_ is six launches,
-        20 us per step; torch.index_select(out=) picks a 42 us small-index kernel).  n_pts: see step()."""
+                     q: int = 1, n_pts: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """step() for device-resident float32 datasets.  Fused path: the step's kernels read rows `idx` (int64,
+        device) of the three tensors in place - nothing is gathered; `packed` (pack_schedule(idx, n_pts)) delivers
+        indices and n_pts with one 136-byte copy.  Autograd path: the rows are gathered into the static buffers by
+        ONE launch (nvf_gather_batch; advanced indexing + copy_ is six launches).  n_pts: see step()."""
         n_rows = int(gt_all.shape[0])
         ok = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == n_rows
                  for t in (emb_all, gt_all, dist_all))
@@ -259,6 +402,15 @@ class WeightStep:
             idx_d = idx.to(emb_all.device)
             return self.step(emb_all.detach()[idx_d], gt_all[idx.to(gt_all.device)], dist_all[idx.to(dist_all.device)],
                              q, n_pts=n_pts)
+        if self.fused:
+            self._idx_src = (emb_all.detach(), gt_all, dist_all)
+            if packed is not None:
+                self._hdr.copy_(packed, non_blocking=True)
+                return self._run(q, None, indexed=True, ext=True)
+            self._idx_buf.copy_(idx, non_blocking=True)
+            if n_pts is None:          # batch-global count from the rows themselves (one reduction + all-reduce)
+                n_pts = D.allreduce_sum_(gt_all[idx].sum())
+            return self._run(q, n_pts, indexed=True)
         _gather_batch(emb_all.detach(), gt_all, dist_all, idx.contiguous(), self.emb, self.gt, self.dist, self.status)
         return self._run(q, n_pts)
 
@@ -272,18 +424,20 @@ class WeightStep:
         self.dist.copy_(dist_, non_blocking=True)
         return self._run(q, n_pts)
 
-    def _run(self, q: int, n_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
-        ext = n_pts is not None
-        if ext:
+    def _run(self, q: int, n_pts: Optional[torch.Tensor] = None, indexed: bool = False, ext: bool = False) -> torch.Tensor:
+        if n_pts is not None:
+            ext = True
             self.n_pts.copy_(n_pts.reshape(1), non_blocking=True)
         if not self.use_graph:
-            self._body(q, ext)
+            self._body(q, ext, indexed)
             return self.stats
         if self.fused_opt:
             self.opt.sync_lr()
-        if (q, ext) not in self._graphs:
-            self._capture(q, ext)
-        self._graphs[(q, ext)].replay()
+        # a captured step holds the addresses of what it reads: the resident dataset is part of the key
+        key = (q, ext, tuple(t.data_ptr() for t in self._idx_src)) if indexed else (q, ext)
+        if key not in self._graphs:
+            self._capture(key, q, ext, indexed)
+        self._graphs[key].replay()
         return self.stats
 
     def check_status(self) -> None:
@@ -479,6 +633,7 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
     cnt = gt_d.reshape(n_leaf, -1).sum(1)
     npts_steps = torch.stack([cnt[b].sum() if b.numel() else cnt.new_zeros(()) for b in batches])
     npts_steps = D.allreduce_sum_(npts_steps).reshape(steps, 1)
+    packed = [wsteps[int(b.numel())].pack_schedule(b, npts_steps[s]) if b.numel() else None for s, b in enumerate(batches)]
     history = []
     acc = torch.zeros(len(STAT_NAMES), device=dev)
     q = 1 if start_epoch < phase_change else 2
@@ -491,7 +646,8 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
             if nb == 0:
                 wstep.empty_step()
                 continue
-            acc += wsteps[nb].step_indexed(emb_local, gt_d, dist_d, batches[s], q=q, n_pts=npts_steps[s])
+            acc += wsteps[nb].step_indexed(emb_local, gt_d, dist_d, batches[s], q=q, n_pts=npts_steps[s],
+                                           packed=packed[s])
         est = estep.step(gt_d, dist_d, q)
         with warnings.catch_warnings():          # the graph replays opt.step(); the schedulers cannot see it
             warnings.simplefilter("ignore", UserWarning)

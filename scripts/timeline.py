@@ -30,14 +30,14 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(3):
-            tw.step(5 + i, False)
+        tw.step(5, False)           # CUPTI warm-up replay
+        torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        tw.step(6, False)           # exactly one replay in this profile
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
-    # split into replays at the gather kernel (first kernel of a step)
-    starts = [i for i, e in enumerate(evs) if "k_gather_batch" in e.name]
-    last = evs[starts[-1]:]
+    last = evs
     t0 = last[0].time_range.start
     lines = []
     busy = {}

@@ -166,6 +166,10 @@ int nvf_train_backward(const NvfDesc* desc, const NvfWeights* w, const float* la
                                           workspace, workspace_bytes);
 }
 int nvf_ffma_microbench(int, int64_t, float*, double*, void*) { return NVF_ERR_NO_DEVICE; }
+// the fused step and its noise generator exist only in the CUDA library
+int nvf_train_step_workspace_bytes(const NvfDesc*, int64_t, size_t*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_train_step(const NvfStepArgs*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_rng_uniform(uint64_t, uint64_t, int, int64_t, int64_t, float*, void*) { return NVF_ERR_UNSUPPORTED; }
 
 
 // parameter-side fused kernels exist only in the CUDA library (the torch ops they replace are the CPU reference)
