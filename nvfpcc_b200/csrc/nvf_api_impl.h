@@ -16,6 +16,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 inline bool is_cfg_A(const NvfDesc& d) { return d.ch == 3 && d.c0 == 8 && d.c1 == 16 && d.c2 == 8 && d.c3 == 8; }
 constexpr int64_t kGenericDecodeChunk = 128;  // blocks per pass of the layer-wise decode path
+constexpr int kQueueSlots = 16;                // work-queue slots (16 bytes each) of one forward / backward pass
 constexpr int kMaxPartialCtas = 304;          // persistent CTAs of a split-K weight-gradient kernel (2 per SM)
 // scratch for the split-K partial results of one backward pass: every weight-gradient kernel
 // writes <= kMaxPartialCtas partial copies of its layer's gradient; per-block partials of the
@@ -53,7 +54,7 @@ struct DecodeWs {
 };
 
 struct TrainWs {
-  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_p2, off_p1, off_p0, off_loss, off_partial, total;
+  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_p2, off_p1, off_p0, off_loss, off_partial, off_queue, total;
   static TrainWs make(const NvfDesc& d, int64_t n) {
     TrainWs L{};
     const Stash s = Stash::make(d);
@@ -72,6 +73,7 @@ struct TrainWs {
     L.off_p0 = take(sizeof(float) * (size_t)512 * n);
     L.off_loss = take(sizeof(double) * (size_t)NVF_LOSS_SUMS * (n * kLossChunks + 1));
     L.off_partial = take(sizeof(float) * partial_floats(d, n));
+    L.off_queue = take(2 * 16 * kQueueSlots);   // forward slots, then backward slots
     L.total = o;
     return L;
   }
@@ -291,6 +293,8 @@ struct Api {
     if (workspace_bytes < W.total) return NVF_ERR_WORKSPACE;
     char* ws = (char*)workspace;
     float* packed = (float*)(ws + W.off_packed);
+    l.zero_queue(ws + W.off_queue, 2 * 16 * kQueueSlots);   // the caller's workspace is not zero-filled on this path
+    l.set_queue(ws + W.off_queue);
     pack_all(l, *desc, *w, packed, true, true);
     forward_layers(l, *desc, *w, packed, latent, (int)n, (float*)(ws + W.off_stash), out, cls1, cls0,
                    (float*)(ws + W.off_p2), (float*)(ws + W.off_p1), (float*)(ws + W.off_p0));
@@ -338,6 +342,7 @@ struct Api {
     const float* gl1 = (const float*)(ws + W.off_gl1);
     const float* gl0 = (const float*)(ws + W.off_gl0);
     l.set_partial((float*)(ws + W.off_partial), partial_floats(d, n));
+    l.set_queue(ws + W.off_queue + 16 * kQueueSlots);
     const bool wg = (flags & NVF_BWD_WGRAD) != 0;
     LayerParams p{};
     if (flags & NVF_BWD_DLOGIT) {

@@ -14,6 +14,7 @@
 #include "nvf_fast_params.cuh"
 #include "nvf_fast_latent.cuh"
 #include "nvf_step.cuh"
+#include "nvf_rows_convt.cuh"
 
 namespace nvf {
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches); shared with nvf_prep.cu
@@ -46,6 +47,15 @@ SidePool g_side[kMaxDevices];
 // slots the side-stream weight-gradient kernels would otherwise fill; with the heavy kernels releasing them only
 // after their main loop (pdl_entry_heavy / pdl_trigger) 0.899 ms vs 0.891 ms - neutral, the captured graph already
 // hides launch latency - so the default stays OFF (plain launches; the PDL instructions are then no-ops).
+// NVF_ROWS=0 switches the row-register-tile kernels (nvf_rows_*.cuh) off and the smem-tile kernels back on (A/B runs)
+bool rows_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVF_ROWS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -316,6 +326,15 @@ struct DevLauncher {
   size_t part_off = 0, part_cap = 0;
   fast::ReduceParams red{};     // pending fixed-order reductions, flushed by flush_reduce()
 
+  // work-queue words of the queue-fed kernels: 16 bytes per launch, zero on entry (the kernels rewind them)
+  unsigned int* queue_base = nullptr;
+  int queue_next = 0;
+  void set_queue(void* base) { queue_base = (unsigned int*)base; queue_next = 0; }
+  void zero_queue(void* base, size_t bytes) { chk(cudaMemsetAsync(base, 0, bytes, st)); }
+  unsigned int* take_queue() {
+    if (!queue_base || queue_next >= kQueueSlots) return nullptr;
+    return queue_base + 4 * (queue_next++);
+  }
   void set_partial(float* base, size_t floats) { part_base = base; part_cap = floats; part_off = 0; }
   float* take_partial(size_t floats) {
     floats = (floats + 63) / 64 * 64;
@@ -374,6 +393,22 @@ struct DevLauncher {
     post();
     return true;
   }
+  template <int CI, int CO, int DIN, int KS, int THREADS, int MINB, bool PIPE = false, bool CHUNK = true>
+  bool convT_fwd_rows(const LayerParams& p) {
+    using G = fast::RowTFwdCfg<CI, CO, DIN, KS>;
+    static_assert(G::SMEM_BYTES <= 226 * 1024 / MINB, "row-tile convT weights");
+    unsigned int* q = take_queue();
+    if (!q) return false;
+    auto* k = fast::k_convT5_fwd_rows<CI, CO, DIN, KS, THREADS, MINB, PIPE, CHUNK>;
+    if (!smem_attr(k, G::SMEM_BYTES)) return true;
+    fast::RowTFwdParams a{p.in, p.out, p.Wp, p.bias, q, p.n};
+    int grid = n_sms * MINB;
+    const int need = (p.n * G::ITEMS_PER_BLOCK + THREADS / 32 - 1) / (THREADS / 32);
+    if (grid > need) grid = need;
+    nvf_launch(k, dim3(grid), dim3(THREADS), (size_t)(G::SMEM_BYTES), st, a);
+    post();
+    return true;
+  }
   template <int CG, int CX, int DIN, int TY, int CGC, int MINB>
   bool convT_dgrad(const LayerParams& p) {
     using G = fast::ConvTDgradCfg<CG, CX, DIN, TY, CGC>;
@@ -422,6 +457,14 @@ struct DevLauncher {
       return false;
     }
     if (p.op == OP_CONVT && p.P == 0 && p.act == ACT_RELU && !p.add && !p.mask && !p.out2) {
+      if (rows_enabled() && queue_base) {
+        bool done = false;
+        // measured on B200 (16-block step): up2 (8,8,16) 60 -> 54 us; up1 (16,8,8) loses (25 -> 33 us: too little
+        // work per warp item against the per-CTA weight staging), so it stays on the tile kernel
+        if (p.CI == 8 && p.CO == 8 && p.Din == 16) done = convT_fwd_rows<8, 8, 16, 2, 256, 2, false, false>(p);
+        else if (p.CI == 16 && p.CO == 16 && p.Din == 16) done = convT_fwd_rows<16, 16, 16, 2, 256, 1>(p);
+        if (done) return true;
+      }
       if (p.CI == 8 && p.CO == 8 && p.Din == 16) return convT_fwd<8, 8, 16, 2>(p);
       if (p.CI == 16 && p.CO == 8 && p.Din == 8) return convT_fwd<16, 8, 8, 2, 4>(p);
       if (p.CI == 16 && p.CO == 16 && p.Din == 16) return convT_fwd<16, 16, 16, 1>(p);
@@ -1060,6 +1103,7 @@ int train_step_impl(DevLauncher& l, const NvfStepArgs& a, void* workspace, size_
   float* p2 = (float*)(tws + T.off_p2);
   float* p1 = (float*)(tws + T.off_p1);
   float* p0 = (float*)(tws + T.off_p0);
+  l.set_queue(tws + T.off_queue);   // zero since the caller's one-time fill; every queue-fed kernel rewinds its words
   Api<DevLauncher>::forward_layers(l, d, w, (const float*)(tws + T.off_packed), latent, n, (float*)(tws + T.off_stash), p2, p1, p0);
 
   // ---- loss, metrics, dL/dlogit, total loss and scalar cotangents: one launch

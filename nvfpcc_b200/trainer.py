@@ -145,6 +145,9 @@ class FusedStepCall:
         import ctypes as C
         L = ops._lib
         self.b = L.cuda_binding()
+        dev = torch.device(dev)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.net, self.dev, self.n = net, dev, int(n)
         rec = net.reconstructor
         ch = rec.in_channels

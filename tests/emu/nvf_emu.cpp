@@ -67,6 +67,8 @@ struct EmuLauncher {
   void side_end() {}
   void join() {}
   void set_partial(float*, size_t) {}
+  void set_queue(void*) {}
+  void zero_queue(void*, size_t) {}
   void flush_reduce() {}
   template <int COT>
   void layer(const LayerParams& p) {
