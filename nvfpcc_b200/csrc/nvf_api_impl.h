@@ -16,6 +16,20 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 inline bool is_cfg_A(const NvfDesc& d) { return d.ch == 3 && d.c0 == 8 && d.c1 == 16 && d.c2 == 8 && d.c3 == 8; }
 constexpr int64_t kGenericDecodeChunk = 128;  // blocks per pass of the layer-wise decode path
+// per-leaf scratch of the two-pass (wide) head: conv2 rows next to the cut + their partial logits
+inline size_t head_brow_floats(const NvfDesc& d) { return d.c3 == 16 ? (size_t)2 * d.c3 * 1024 : 0; }
+inline size_t head_pl_floats(const NvfDesc& d) { return d.c3 == 16 ? (size_t)2048 : 0; }
+// blocks per pass of the fused-head decode path: as many whole waves of 148 persistent CTAs as fit 3 GiB of
+// stem activations (8,16,8,8: 0.6 MB per block; 16,32,16,16: 1.2 MB), so a cloud is normally one pass and no SM
+// idles at a chunk boundary
+inline int64_t head_chunk(const NvfDesc& d, int64_t n) {
+  const int64_t per_block = 4 * (Stash::make(d).a4 + (int64_t)d.c2 * 16 * 480 + (int64_t)head_brow_floats(d) + (int64_t)head_pl_floats(d));
+  int64_t c = ((int64_t)3 << 30) / per_block / 148 * 148;
+  if (c < 148) c = 148;
+  return n < c ? n : c;
+}
+// configurations the warp-specialised fused decode head (nvf_decode_head.cuh) is instantiated for
+inline bool head_cfg(const NvfDesc& d) { return (d.c2 == 8 && d.c3 == 8) || (d.c2 == 16 && d.c3 == 16); }
 constexpr int kQueueSlots = 16;                // work-queue slots (16 bytes each) of one forward / backward pass
 constexpr int kMaxPartialCtas = 304;          // persistent CTAs of a split-K weight-gradient kernel (2 per SM)
 // scratch for the split-K partial results of one backward pass: every weight-gradient kernel
@@ -31,14 +45,24 @@ inline size_t partial_floats(const NvfDesc& d, int64_t n) {
 }
 
 struct DecodeWs {
-  size_t off_packed, off_scratch, off_mask, off_offsets, total;
-  static DecodeWs make(const NvfDesc& d, int64_t n) {
+  size_t off_packed, off_scratch, off_sp, off_brow, off_pl, off_mask, off_offsets, total;
+  // head: stem layers batched over a chunk of blocks (stash up to conv1's output), then the fused head kernel
+  static DecodeWs make(const NvfDesc& d, int64_t n, bool head) {
     DecodeWs L{};
     size_t o = 0;
     L.off_packed = o;
     o += align_up(sizeof(float) * (size_t)GenericPacked::floats(d));
     L.off_scratch = o;
-    if (is_cfg_A(d)) {
+    if (head) {
+      const int64_t chunk = head_chunk(d, n);
+      o += align_up(sizeof(float) * (size_t)Stash::make(d).a4 * (size_t)chunk);
+      L.off_sp = o;
+      o += align_up(sizeof(float) * (size_t)d.c2 * 16 * 480 * (size_t)chunk);
+      L.off_brow = o;
+      o += align_up(sizeof(float) * head_brow_floats(d) * (size_t)chunk);
+      L.off_pl = o;
+      o += align_up(sizeof(float) * head_pl_floats(d) * (size_t)chunk);
+    } else if (is_cfg_A(d)) {
       o += align_up(sizeof(float) * (size_t)FusedA::SCRATCH_FLOATS * kMaxCtas);
     } else {
       const int64_t chunk = n < kGenericDecodeChunk ? n : kGenericDecodeChunk;
@@ -77,6 +101,17 @@ struct TrainWs {
     L.total = o;
     return L;
   }
+};
+
+// arguments of the fused decode head (mirrors fast::HeadParams, which only the CUDA build sees)
+struct HeadArgs {
+  const float *sp, *w_up2, *w_c2, *w_cls, *up2_b, *conv2_b, *cls2_b;
+  float* prob_out;
+  uint32_t* mask_out;
+  int32_t* counts_out;
+  float *brow, *pl;
+  float thh;
+  int32_t n_blocks;
 };
 
 template <class L>
@@ -147,7 +182,7 @@ struct Api {
   // p2/p1/p0: optional second copies of the three heads' probabilities (kept for the backward pass)
   static void forward_layers(L& l, const NvfDesc& d, const NvfWeights& w, const float* packed, const float* latent,
                              int n, float* stash, float* out, float* cls1, float* cls0, float* p2 = nullptr,
-                             float* p1 = nullptr, float* p0 = nullptr) {
+                             float* p1 = nullptr, float* p0 = nullptr, bool stem_only = false) {
     const Stash s = Stash::make(d);
     const GenericPacked g = GenericPacked::make(d);
     // NOTE: the stash is laid out tensor-major ([tensor][n][...]) so that every layer sees a dense batch.
@@ -184,6 +219,10 @@ struct Api {
       layer(l, p);
       l.side_end();
     }
+    if (stem_only) {   // the fused decode head takes over from conv1's output
+      l.join();
+      return;
+    }
     // up2: convT k5 s2 p0 + ReLU (:4712-4719, :4765)
     p = LayerParams{a3, a4, packed + g.up2, w.up2_b, nullptr, nullptr, n, d.c2, d.c3, 16, 16, 35, 36, 0, ACT_RELU, OP_CONVT};
     layer(l, p);
@@ -204,14 +243,38 @@ struct Api {
     if (n_blocks > 0 && (!latent || !counts_out)) return NVF_ERR_INVALID_ARG;  // empty input: nothing to read
     if (n_blocks > 0x7fffffff / 1024) return NVF_ERR_INVALID_ARG;
     if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
-    const DecodeWs W = DecodeWs::make(*desc, n_blocks);
+    const bool head = l.has_head(*desc);
+    const DecodeWs W = DecodeWs::make(*desc, n_blocks, head);
     if (workspace_bytes < W.total) return NVF_ERR_WORKSPACE;
     char* ws = (char*)workspace;
     float* packed = (float*)(ws + W.off_packed);
     uint32_t* mask = mask_out ? mask_out : (uint32_t*)(ws + W.off_mask);
     int64_t* offsets = (int64_t*)(ws + W.off_offsets);
     if (n_blocks > 0) {
-      if (is_cfg_A(*desc)) {
+      if (head) {
+        // stem (up0 .. conv1, 13 % of the multiply-adds) as batched layer kernels over a chunk of blocks, then
+        // one persistent fused kernel per chunk for up2 -> conv2 -> conv2_cls -> sigmoid -> threshold
+        const GenericPacked g = GenericPacked::make(*desc);
+        pack_all(l, *desc, *w, packed, false, false);
+        PackParams pp{};
+        pp.job[pp.njobs++] = PackJob{w->cls2_w, packed + g.fusedA, PACK_CLS_IS, 1, desc->c3, 3};
+        l.pack(pp);
+        const int64_t chunk = head_chunk(*desc, n_blocks);
+        float* stash = (float*)(ws + W.off_scratch);
+        float* sp = (float*)(ws + W.off_sp);
+        l.zero_ints(counts_out, n_blocks);
+        for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+          const int nb = (int)(n_blocks - b0 < chunk ? n_blocks - b0 : chunk);
+          forward_layers(l, *desc, *w, packed, latent + b0 * desc->ch * 8, nb, stash, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, true);
+          l.pad_conv1(stash + Stash::make(*desc).a3 * nb, sp, (int64_t)nb * desc->c2 * 16);
+          HeadArgs ha{sp, packed + g.up2, packed + g.conv2, packed + g.fusedA, w->up2_b, w->conv2_b, w->cls2_b,
+                      prob_out ? prob_out + b0 * kVox : nullptr, mask + b0 * 1024, counts_out + b0,
+                      (float*)(ws + W.off_brow), (float*)(ws + W.off_pl), thh, nb};
+          // always one CTA per SM: with fewer (leaf, pass) units than SMs the kernel cuts them along z
+          l.head(*desc, ha, l.sms() < kMaxCtas ? l.sms() : kMaxCtas);
+        }
+      } else if (is_cfg_A(*desc)) {
         float* pk = packed + GenericPacked::make(*desc).fusedA;
         PackParams pp{};
         pp.job[pp.njobs++] = PackJob{w->conv0_w, pk + FusedA::P_CONV0, PACK_CONVT_FWD, 8, 16, 5};

@@ -15,6 +15,7 @@
 #include "nvf_fast_latent.cuh"
 #include "nvf_step.cuh"
 #include "nvf_rows_convt.cuh"
+#include "nvf_decode_head.cuh"
 
 namespace nvf {
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches); shared with nvf_prep.cu
@@ -52,6 +53,16 @@ bool rows_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NVF_ROWS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// NVF_DECODE_HEAD=0 switches the warp-specialised fused decode head off (round-1 phase kernel for 8,16,8,8, layer
+// kernels otherwise) for A/B runs
+bool head_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVF_DECODE_HEAD");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -292,6 +303,32 @@ struct DevLauncher {
     }
     nvf_launch(k_decode_fused_A, dim3(grid), dim3(kThreads), (size_t)(FusedA::SMEM_BYTES), st, p);
     post();
+  }
+  bool has_head(const NvfDesc& d) { return head_enabled() && head_cfg(d); }
+  void zero_ints(int32_t* p, int64_t n) { chk(cudaMemsetAsync(p, 0, sizeof(int32_t) * (size_t)n, st)); }
+  void pad_conv1(const float* src, float* dst, int64_t planes) {
+    int64_t grid = (planes * (fast::kSpPlane / 4) + 255) / 256;
+    if (grid > (int64_t)n_sms * 16) grid = (int64_t)n_sms * 16;
+    nvf_launch(fast::k_pad_conv1, dim3((unsigned)grid), dim3(256), (size_t)0, st, src, dst, (long long)planes);
+    post();
+  }
+  template <int C2, int C3>
+  void head_t(const HeadArgs& a, int grid) {
+    using G = fast::HeadCfg<C2, C3>;
+    auto* k = fast::k_decode_head<C2, C3>;
+    if (!smem_attr(k, G::SMEM_BYTES)) return;
+    fast::HeadParams p{a.sp, a.w_up2, a.w_c2, a.w_cls, a.up2_b, a.conv2_b, a.cls2_b, a.prob_out, a.mask_out,
+                       a.counts_out, G::COH == 2 ? a.brow : nullptr, G::COH == 2 ? a.pl : nullptr, a.thh, a.n_blocks};
+    nvf_launch(k, dim3(grid), dim3(fast::kHeadThreads), (size_t)G::SMEM_BYTES, st, p);
+    post();
+    if (G::COH == 2) {
+      nvf_launch(fast::k_head_fixup<C3>, dim3(a.n_blocks), dim3(256), (size_t)0, st, p);
+      post();
+    }
+  }
+  void head(const NvfDesc& d, const HeadArgs& a, int grid) {
+    if (d.c3 == 8) head_t<8, 8>(a, grid);
+    else head_t<16, 16>(a, grid);
   }
   void scan(const EmitParams& p) { nvf_launch(k_scan_counts, dim3(1), dim3(kThreads), (size_t)(0), st, p); post(); }
   void emit(const EmitParams& p, int grid) { nvf_launch(k_emit_coords, dim3(grid), dim3(kThreads), (size_t)(0), st, p); post(); }
@@ -667,12 +704,12 @@ int nvf_last_cuda_error(void) { return g_last_cuda; }
 
 long long nvf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int nvf_has_fused_decode(const NvfDesc* desc) { return desc && is_cfg_A(*desc) ? 1 : 0; }
+int nvf_has_fused_decode(const NvfDesc* desc) { return desc && ((head_enabled() && head_cfg(*desc)) || is_cfg_A(*desc)) ? 1 : 0; }
 
 int nvf_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, int mode, size_t* bytes_out) {
   if (!desc || !bytes_out || n_blocks < 0) return NVF_ERR_INVALID_ARG;
   if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
-  if (mode == NVF_MODE_DECODE) *bytes_out = DecodeWs::make(*desc, n_blocks).total;
+  if (mode == NVF_MODE_DECODE) *bytes_out = DecodeWs::make(*desc, n_blocks, head_enabled() && head_cfg(*desc)).total;
   else if (mode == NVF_MODE_TRAIN) *bytes_out = TrainWs::make(*desc, n_blocks).total;
   else return NVF_ERR_INVALID_ARG;
   return NVF_OK;

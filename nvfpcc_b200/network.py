@@ -337,15 +337,24 @@ class CompDecoder(nn.Module):
         out, cls1, cls0 = ops.nvf_decoder(self.in_channels, self.channels, x, w)
         return out, [cls0, cls1, out], net_bits
 
+    def _decode_weights(self, q):
+        """Effective tensors for the decode-only calls: on the GPU one fused parameter kernel (nvf_param_prep, the same
+        arithmetic as `effective_weights`: round(k*16)/16 + kernel_init is exact) instead of ~150 elementwise launches."""
+        if self.up0.kernel.is_cuda and q != 1:
+            w, _ = ops.decoder_params(self.in_channels, self.channels, q, self.raw_tensors(), self.activation.beta_bound,
+                                      self.activation.gamma_bound, float(self.activation.reparam_pedestal))
+            return w
+        return self.effective_weights(q, aux=False)
+
     @torch.no_grad()
     def reconstruct(self, x, q=2):
-        r = ops.decode_blocks(self.in_channels, self.channels, self.effective_weights(q, aux=False), x, None, 2.0,
+        r = ops.decode_blocks(self.in_channels, self.channels, self._decode_weights(q), x, None, 2.0,
                               return_prob=True, return_host=False)
         return r["prob"]
 
     @torch.no_grad()
     def decode_points(self, x, origins, thh, q=2, return_prob=False, return_host=None, timing=None):
-        return ops.decode_blocks(self.in_channels, self.channels, self.effective_weights(q, aux=False), x, origins,
+        return ops.decode_blocks(self.in_channels, self.channels, self._decode_weights(q), x, origins,
                                  thh, return_prob=return_prob, return_host=return_host, timing=timing)
 
     def get_bits(self):

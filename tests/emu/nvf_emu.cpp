@@ -63,6 +63,11 @@ struct EmuLauncher {
                      float*, float*, float*, float*, float*) { return false; }
   bool fast_stem_bwd(const NvfDesc&, const NvfWeights&, const float*, int, const float*, const float*, const float*,
                      float*, const NvfWeightGrads*, float*) { return false; }
+  // the warp-specialised fused decode head is CUDA-only: the emulator runs the round-1 phase kernel / layer kernels
+  bool has_head(const NvfDesc&) { return false; }
+  void zero_ints(int32_t*, int64_t) {}
+  void pad_conv1(const float*, float*, int64_t) {}
+  void head(const NvfDesc&, const HeadArgs&, int) {}
   void side_begin() {}
   void side_end() {}
   void join() {}
@@ -126,7 +131,7 @@ int nvf_has_fused_decode(const NvfDesc* desc) { return desc && is_cfg_A(*desc) ?
 int nvf_workspace_bytes(const NvfDesc* desc, int64_t n_blocks, int mode, size_t* bytes_out) {
   if (!desc || !bytes_out || n_blocks < 0) return NVF_ERR_INVALID_ARG;
   if (!generic_supported(*desc)) return NVF_ERR_UNSUPPORTED;
-  if (mode == NVF_MODE_DECODE) *bytes_out = DecodeWs::make(*desc, n_blocks).total;
+  if (mode == NVF_MODE_DECODE) *bytes_out = DecodeWs::make(*desc, n_blocks, false).total;
   else if (mode == NVF_MODE_TRAIN) *bytes_out = TrainWs::make(*desc, n_blocks).total;
   else return NVF_ERR_INVALID_ARG;
   return NVF_OK;
