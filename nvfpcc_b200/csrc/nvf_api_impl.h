@@ -182,7 +182,8 @@ struct Api {
   // p2/p1/p0: optional second copies of the three heads' probabilities (kept for the backward pass)
   static void forward_layers(L& l, const NvfDesc& d, const NvfWeights& w, const float* packed, const float* latent,
                              int n, float* stash, float* out, float* cls1, float* cls0, float* p2 = nullptr,
-                             float* p1 = nullptr, float* p0 = nullptr, bool stem_only = false) {
+                             float* p1 = nullptr, float* p0 = nullptr, bool stem_only = false,
+                             float* pad_scratch = nullptr) {
     const Stash s = Stash::make(d);
     const GenericPacked g = GenericPacked::make(d);
     // NOTE: the stash is laid out tensor-major ([tensor][n][...]) so that every layer sees a dense batch.
@@ -208,7 +209,8 @@ struct Api {
     }
     // up1: convT k5 s2 p0 + ReLU (:4693-4700, :4762)
     p = LayerParams{a1, a2, packed + g.up1, w.up1_b, nullptr, nullptr, n, d.c1, d.c2, 8, 8, 19, 20, 0, ACT_RELU, OP_CONVT};
-    layer(l, p);
+    // decode (many leaves): polyphase kernel on a zero-padded copy of conv0's output; else the tile kernels
+    if (!(pad_scratch && l.up1_poly(p, pad_scratch))) layer(l, p);
     // conv1: conv k4 + ReLU (:4702-4710, :4763)
     p = LayerParams{a2, a3, packed + g.conv1, w.conv1_b, nullptr, nullptr, n, d.c2, d.c2, 19, 20, 16, 16, 0, ACT_RELU, OP_CORR4};
     layer(l, p);
@@ -266,7 +268,7 @@ struct Api {
         for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk) {
           const int nb = (int)(n_blocks - b0 < chunk ? n_blocks - b0 : chunk);
           forward_layers(l, *desc, *w, packed, latent + b0 * desc->ch * 8, nb, stash, nullptr, nullptr, nullptr, nullptr,
-                         nullptr, nullptr, true);
+                         nullptr, nullptr, true, sp);   // sp doubles as the padded conv0 output until conv1 is done
           l.pad_conv1(stash + Stash::make(*desc).a3 * nb, sp, (int64_t)nb * desc->c2 * 16);
           HeadArgs ha{sp, packed + g.up2, packed + g.conv2, packed + g.fusedA, w->up2_b, w->conv2_b, w->cls2_b,
                       prob_out ? prob_out + b0 * kVox : nullptr, mask + b0 * 1024, counts_out + b0,

@@ -326,13 +326,13 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
 // of parity CY in a slice with NKZ valid kz taps: kz = kz0 + 2 jz reads the input slice jz before the first one,
 // ky = CY + 2 jy the input row jy above - compile-time offsets, so the loop is branch-free and the compiler can
 // issue the loads of later steps under the FFMA2s of earlier ones.
-template <int C3, int CY, int NKZ>
+template <int C3, int CY, int NKZ, int PLANE = kSpPlane, int PITCH = kSpPitch>
 __device__ __forceinline__ void head_up2_channel(p2 (&acc)[4][8], const float* in, const float* w) {
 #pragma unroll
   for (int jz = 0; jz < NKZ; ++jz) {
 #pragma unroll
     for (int jy = 0; jy < (CY ? 2 : 3); ++jy) {
-      const float* r = in - jz * kSpPlane - jy * kSpPitch;
+      const float* r = in - jz * PLANE - jy * PITCH;
       float a0, a1;
       ld2(r, a0, a1);
       const f4 v = ld4(r + 2);
@@ -539,6 +539,138 @@ __global__ void __launch_bounds__(256) k_head_fixup(HeadParams p) {
     }
   }
   if (cnt) atomicAdd(p.counts_out + b, cnt);
+}
+
+// [planes][DIN][DIN] -> zero-padded [planes][DIN+4][DIN+8], data at rows 2.., columns 4.. (one float4 of the
+// destination per thread): the layout the polyphase transposed-conv tiles read their 6-float windows from
+template <int DIN>
+__global__ void __launch_bounds__(256) k_pad_in(const float* __restrict__ src, float* __restrict__ dst, long long planes) {
+  pdl_entry();
+  constexpr int ROWS = DIN + 4, P4 = (DIN + 8) / 4, PL4 = ROWS * P4;
+  const long long total = planes * PL4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pl = i / PL4;
+    const int r4 = (int)(i - pl * PL4);
+    const int row = r4 / P4, c4 = r4 - row * P4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 2 && row < DIN + 2 && c4 >= 1 && c4 <= DIN / 4)
+      v = __ldg(reinterpret_cast<const float4*>(src + pl * (DIN * DIN) + (row - 2) * DIN + (c4 - 1) * 4));
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+}
+
+// Stand-alone polyphase k=5 stride-2 transposed conv + ReLU over many leaves (the decode stem's up1): the head
+// producer's thread tile (8 x = 4 even + 4 odd outputs, 8 output channels, all taps of one input channel unrolled)
+// with one warp per (output slice, row parity, channel group).  A CTA of four warps works on one slice (two channel
+// groups) or two adjacent slices (one group) and streams the weights of one input channel at a time through a
+// two-stage cp.async ring, so its shared memory is 2 x 125 x CO floats and several CTAs share an SM.
+template <int CI, int CO, int DIN>
+struct PolyCfg {
+  static_assert(CO == 8 || CO == 16, "channel groups of 8");
+  static constexpr int DOUT = 2 * DIN + 3, OP = (DOUT + 3) / 4 * 4;
+  static constexpr int PROWS = DIN + 4, PPITCH = DIN + 8, PPLANE = PROWS * PPITCH;
+  static constexpr int COH = CO / 8, NSL = 2 / COH;        // slices per CTA item
+  static constexpr int NE = (DOUT + 1) / 2, NO = DOUT / 2, XT = (DOUT + 7) / 8;
+  static constexpr int IPL = (DOUT + NSL - 1) / NSL;       // items per leaf
+  static constexpr int STAGE = 125 * CO;
+  static constexpr bool RING = CI * STAGE * 4 > 72 * 1024;   // else all weights stay resident and the warps never meet
+  static constexpr int SMEM_BYTES = (RING ? 2 : CI) * STAGE * 4;
+  static constexpr int MINB = RING ? 4 : 3;
+  static_assert(NE * XT <= 32, "one warp per (slice, row parity, channel group)");
+};
+
+struct PolyParams {
+  const float* inp;    // padded input [n][CI][DIN][DIN+4][DIN+8]
+  float* out;          // [n][CO][DOUT][DOUT][OP], columns >= DOUT written as zero
+  const float* w;      // [CI][5][5][5][CO]
+  const float* bias;   // [CO]
+  int32_t n;
+};
+
+template <int CI, int CO, int DIN>
+__global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_poly(PolyParams p) {
+  pdl_entry();
+  using G = PolyCfg<CI, CO, DIN>;
+  extern __shared__ __align__(128) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cy = warp >> 1;                                 // row parity of this warp
+  const int coh = G::COH == 2 ? (warp & 1) : 0;
+  const int nrows = cy ? G::NO : G::NE;
+  const bool lane_ok = lane < nrows * G::XT;
+  const int q = lane_ok ? lane % G::XT : 0, rr = lane_ok ? lane / G::XT : 0;
+  const int l = 2 * rr + cy;                                // output row
+  uint32_t ring_step = 0;
+  for (int i = tid; i < (G::RING ? 1 : CI) * G::STAGE / 4; i += 128) tma::cp_async16(sm + 4 * i, p.w + 4 * i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (!G::RING) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  const int total = p.n * G::IPL;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int b = item / G::IPL;
+    const int s = (item - b * G::IPL) * G::NSL + (G::NSL == 2 ? (warp & 1) : 0);   // output slice of this warp
+    const bool active = lane_ok && s < G::DOUT;
+    // valid kz taps: kz = kz0, kz0+2, .. with 0 <= (s - kz) / 2 <= DIN-1
+    int kz0 = s & 1;
+    while (s - kz0 > 2 * (DIN - 1)) kz0 += 2;
+    int nkz = 0;
+    for (int kz = kz0; kz < 5 && kz <= s; kz += 2) ++nkz;
+    p2 acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[c][j] = p2_bcast(0.f);
+    const float* in_t = p.inp + (size_t)b * CI * DIN * G::PPLANE +
+                        ((size_t)((s - kz0) >> 1) * G::PROWS + (((l - cy) >> 1) + 2)) * G::PPITCH + 4 * q + 2;
+    const int w_off = ((kz0 * 5 + cy) * 5) * CO + coh * 8;
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+      const float* w_c;
+      if (G::RING) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // stage ring_step & 1 holds channel ci; the other is free
+        const int nci = ci + 1 < CI ? ci + 1 : 0;
+        float* dst = sm + ((ring_step + 1) & 1) * G::STAGE;
+        const float* src = p.w + (size_t)nci * G::STAGE;
+        for (int i = tid; i < G::STAGE / 4; i += 128) tma::cp_async16(dst + 4 * i, src + 4 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        w_c = sm + (ring_step & 1) * G::STAGE + w_off;
+        ++ring_step;
+      } else {
+        w_c = sm + ci * G::STAGE + w_off;
+      }
+      if (!active) continue;
+      const float* in_c = in_t + (size_t)ci * DIN * G::PPLANE;
+      if (cy == 0) {
+        if (nkz == 3) head_up2_channel<CO, 0, 3, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+        else if (nkz == 2) head_up2_channel<CO, 0, 2, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+        else head_up2_channel<CO, 0, 1, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+      } else {
+        if (nkz == 3) head_up2_channel<CO, 1, 3, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+        else if (nkz == 2) head_up2_channel<CO, 1, 2, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+        else head_up2_channel<CO, 1, 1, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int co = coh * 8 + c;
+        const float bb = __ldg(p.bias + co);
+        float* o = p.out + (((size_t)b * CO + co) * G::DOUT + s) * G::DOUT * G::OP + (size_t)l * G::OP + 8 * q;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float r = relu(((c & 1) ? p2_hi(acc[c >> 1][j]) : p2_lo(acc[c >> 1][j])) + bb);
+          v[j] = 8 * q + j < G::DOUT ? r : 0.f;
+        }
+        st4(o, v[0], v[1], v[2], v[3]);
+        if (8 * q + 4 < G::OP) st4(o + 4, v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // conv1 output [n][C][16][16][16] -> zero-padded [n][C][16][20][24] (one float4 of the destination per thread)
