@@ -183,7 +183,7 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
     float* brow = G::COH == 2 ? p.brow + ((size_t)b * 2 + yh) * C3 * 1024 : nullptr;
     int cnt = 0;
     p2 acc[4][4][4];                             // [slot j: conv2 slice s-3+j][channel pair][x]
-    float cacc[3][4];                            // [slot g: logit slice z1-1+g][x]
+    p2 cacc[3][2];                               // [slot g: logit slice z1-1+g][x pair] (lo = even x)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -191,9 +191,7 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][c][i] = p2_bcast(0.f);
 #pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cacc[g][i] = 0.f;
+    for (int g = 0; g < 3; ++g) cacc[g][0] = cacc[g][1] = p2_bcast(0.f);
 
 #pragma unroll 1
     for (int s = zc_lo; s <= zc_hi + 3; ++s, ++it) {   // up2 slices of this item
@@ -252,25 +250,29 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
           for (int ky = 0; ky < 3; ++ky) {
             const float* r = C + ci * G::C_PLANE + (y + ky) * G::C_PITCH + x0 + 3;
             const f4 v = ld4(r + 1);
-            const float a[6] = {r[0], v.x, v.y, v.z, v.w, r[5]};
+            // x pairs of the six-wide window: FFMA2 with the tap weight as the scalar operand; per output the
+            // taps are still added in the order kx = 0, 1, 2
+            const float a0 = r[0], a5 = r[5];
+            const p2 A[5] = {p2_make(a0, v.x), p2_make(v.x, v.y), p2_make(v.y, v.z), p2_make(v.z, v.w), p2_make(v.w, a5)};
             const float* wr = Wcls + (ci * 3 + ky) * 12;
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
               if (g < lo || g > hi) continue;
               const f4 w = ld4(wr + (2 - g) * 4);
+              const p2 wx = p2_bcast(w.x), wy = p2_bcast(w.y), wz = p2_bcast(w.z);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                cacc[g][i] = fmaf(w.x, a[i], cacc[g][i]);
-                cacc[g][i] = fmaf(w.y, a[i + 1], cacc[g][i]);
-                cacc[g][i] = fmaf(w.z, a[i + 2], cacc[g][i]);
+              for (int h = 0; h < 2; ++h) {
+                p2_fma(cacc[g][h], A[2 * h], wx);
+                p2_fma(cacc[g][h], A[2 * h + 1], wy);
+                p2_fma(cacc[g][h], A[2 * h + 2], wz);
               }
             }
           }
         }
         if (G::COH == 2 && coh == 1) {           // hand the second group's finished partial logits to the first
           float* ex = sm + G::OFF_EX + y * 32 + x0;
-          if (z1 - 1 >= za) st4(ex, cacc[0][0], cacc[0][1], cacc[0][2], cacc[0][3]);
-          if (z1 == 31) st4(ex + G::RY * 32, cacc[1][0], cacc[1][1], cacc[1][2], cacc[1][3]);
+          if (z1 - 1 >= za) st4(ex, p2_lo(cacc[0][0]), p2_hi(cacc[0][0]), p2_lo(cacc[0][1]), p2_hi(cacc[0][1]));
+          if (z1 == 31) st4(ex + G::RY * 32, p2_lo(cacc[1][0]), p2_hi(cacc[1][0]), p2_lo(cacc[1][1]), p2_hi(cacc[1][1]));
         }
       }
       named_bar_sync(1, kHeadConsumers);         // C has been read by everyone; partial logits exchanged
@@ -280,9 +282,7 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
           for (int e = 0; e < 2; ++e) {
             if (e == 0 ? z1 - 1 < za : z1 != 31) continue;
             const int zl = e == 0 ? z1 - 1 : 31;   // logit slice that is complete now
-            float v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = cacc[e][i];
+            float v[4] = {p2_lo(cacc[e][0]), p2_hi(cacc[e][0]), p2_lo(cacc[e][1]), p2_hi(cacc[e][1])};
             if (G::COH == 2) {
               const f4 o = ld4(sm + G::OFF_EX + e * G::RY * 32 + y * 32 + x0);
               v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
@@ -310,10 +310,10 @@ __device__ __forceinline__ void head_consumer(const HeadParams& p, float* sm, ui
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          cacc[0][i] = cacc[1][i];
-          cacc[1][i] = cacc[2][i];
-          cacc[2][i] = 0.f;
+        for (int h = 0; h < 2; ++h) {
+          cacc[0][h] = cacc[1][h];
+          cacc[1][h] = cacc[2][h];
+          cacc[2][h] = p2_bcast(0.f);
         }
       }
     }
@@ -353,6 +353,42 @@ __device__ __forceinline__ void head_up2_channel(p2 (&acc)[4][8], const float* i
         }
       }
     }
+  }
+}
+
+// The same step with the kz taps in a run-time loop: a third of the code (the six fully unrolled variants of
+// head_up2_channel are 86 KB of SASS, and warps of the stand-alone kernel that sit in different variants starve on
+// instruction fetch: "no instruction" was its top stall), at the price of one load bubble per kz tap.  Inside the
+// head kernel the unrolled variants win (measured: 9.03 vs 9.35 ms at 8,16,8,8; 36.6 vs 40.4 ms at 16,32,16,16).
+template <int C3, int CY, int PLANE, int PITCH>
+__device__ __forceinline__ void up2_channel_loop(p2 (&acc)[4][8], const float* in, const float* w, int nkz) {
+#pragma unroll 1
+  for (int jz = 0; jz < nkz; ++jz) {
+#pragma unroll
+    for (int jy = 0; jy < (CY ? 2 : 3); ++jy) {
+      const float* r = in - jy * PITCH;
+      float a0, a1;
+      ld2(r, a0, a1);
+      const f4 v = ld4(r + 2);
+      const p2 a[6] = {p2_bcast(a0), p2_bcast(a1), p2_bcast(v.x), p2_bcast(v.y), p2_bcast(v.z), p2_bcast(v.w)};
+      const float* wrow = w + (2 * jy * 5) * C3;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        p2 wv[4];
+        p2_load_w8(wrow + kx * C3, wv);
+        const int h = kx >> 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((kx & 1) == 0) p2_fma(acc[c][2 * j], wv[c], a[j + 2 - h]);
+            else p2_fma(acc[c][2 * j + 1], wv[c], a[j + 2 - h]);
+          }
+        }
+      }
+    }
+    in -= PLANE;
+    w += 50 * C3;
   }
 }
 
@@ -643,15 +679,8 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
       }
       if (!active) continue;
       const float* in_c = in_t + (size_t)ci * DIN * G::PPLANE;
-      if (cy == 0) {
-        if (nkz == 3) head_up2_channel<CO, 0, 3, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-        else if (nkz == 2) head_up2_channel<CO, 0, 2, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-        else head_up2_channel<CO, 0, 1, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-      } else {
-        if (nkz == 3) head_up2_channel<CO, 1, 3, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-        else if (nkz == 2) head_up2_channel<CO, 1, 2, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-        else head_up2_channel<CO, 1, 1, G::PPLANE, G::PPITCH>(acc, in_c, w_c);
-      }
+      if (cy == 0) up2_channel_loop<CO, 0, G::PPLANE, G::PPITCH>(acc, in_c, w_c, nkz);
+      else up2_channel_loop<CO, 1, G::PPLANE, G::PPITCH>(acc, in_c, w_c, nkz);
     }
     if (active) {
 #pragma unroll
