@@ -267,6 +267,28 @@ int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   const float* lr, float beta1, float beta2, float eps, void* stream);
 
 /*
+ * Data-parallel weight loop (NVFPCC.py:154,161,222 with one process per GPU): the all-reduce of the flat
+ * shared-weight gradient FUSED with nvf_adam_step, over NVLink / NVSwitch peer memory instead of an NCCL call plus two
+ * launches.  Every rank allocates one symmetric buffer with nvf_symm_alloc (cudaMalloc + a 64-byte CUDA IPC handle
+ * the host code exchanges, e.g. with torch.distributed.all_gather_object) and maps its peers' buffers with
+ * nvf_symm_open; bytes >= nvf_symm_bytes(n).  nvf_adam_allreduce_step then does, in ONE kernel per rank: copy the
+ * rank's gradient into its buffer, publish a sequence flag to every peer (st.release.sys), wait for all peers'
+ * flags, read the `world` gradients over NVLink, add them in rank order (bit-identical weights on every rank) and
+ * apply the Adam update of nvf_adam_step (same arithmetic; `step` is advanced by the call).
+ *   peers [world] host array: peers[r] = rank r's buffer as mapped in this process (peers[rank] = own buffer)
+ *   ctl   16 zero-initialised device bytes owned by the caller (sequence number + tickets), one per optimizer
+ * Every rank must make the same sequence of calls (as with any collective).  world <= 16, one node.
+ */
+size_t nvf_symm_bytes(int64_t n);
+int nvf_symm_alloc(size_t bytes, void** ptr_out, void* handle64_out);
+int nvf_symm_open(const void* handle64, void** ptr_out);
+int nvf_symm_close(void* ptr);
+int nvf_symm_free(void* ptr);
+int nvf_adam_allreduce_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* step,
+                            const float* lr, float beta1, float beta2, float eps, void* const* peers, int rank,
+                            int world, void* ctl, void* stream);
+
+/*
  * One weight-loop step of train() as ONE call (NVFPCC.py:149-197 up to `loss.backward()`): latent head ->
  * parameter transforms -> decoder forward -> rate-distortion loss -> backward of all of it, with the gradients
  * of the RAW trainable tensors written to caller-chosen destinations (slices of one flat gradient buffer, so the

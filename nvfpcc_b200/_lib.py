@@ -34,6 +34,7 @@ EXPORTS = (
     "nvf_ffma_microbench", "nvf_param_prep", "nvf_param_prep_backward",
     "nvf_latent_forward", "nvf_latent_backward", "nvf_rd_total", "nvf_rd_total_backward", "nvf_adam_step",
     "nvf_train_step_workspace_bytes", "nvf_train_step", "nvf_rng_uniform",
+    "nvf_symm_bytes", "nvf_symm_alloc", "nvf_symm_open", "nvf_symm_close", "nvf_symm_free", "nvf_adam_allreduce_step",
 )
 LATENT_FIELDS = ("kernel", "kernel_init", "b", "b_init", "gdn_beta", "gdn_gamma", "sigma", "mu")   # NvfLatentParams
 LATENT_GRAD_FIELDS = ("kernel", "b", "gdn_beta", "gdn_gamma", "sigma", "mu")                         # NvfLatentGrads
@@ -146,6 +147,13 @@ class Binding:
         L.nvf_rd_total.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]
         L.nvf_rd_total_backward.argtypes = [vp, vp, f32, f32, f32, f32, vp, vp, vp, vp]
         L.nvf_adam_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, f32, f32, f32, vp]
+        L.nvf_symm_bytes.argtypes, L.nvf_symm_bytes.restype = [C.c_int64], C.c_size_t
+        L.nvf_symm_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+        L.nvf_symm_open.argtypes = [vp, C.POINTER(vp)]
+        L.nvf_symm_close.argtypes = [vp]
+        L.nvf_symm_free.argtypes = [vp]
+        L.nvf_adam_allreduce_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, f32, f32, f32, C.POINTER(vp), C.c_int,
+                                              C.c_int, vp, vp]
         L.nvf_train_step_workspace_bytes.argtypes = [C.POINTER(NvfDesc), C.c_int64, C.POINTER(C.c_size_t)]
         L.nvf_train_step.argtypes = [C.POINTER(NvfStepArgs), vp, C.c_size_t, vp]
         L.nvf_rng_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int64, C.c_int64, vp, vp]
@@ -458,6 +466,33 @@ class Binding:
                                     _ptr(step), _ptr(lr), float(beta1), float(beta2), float(eps),
                                     self._stream(param.device))
         self.check(rc, "nvf_adam_step")
+
+    # ---- symmetric (peer-mapped) gradient buffers + fused all-reduce / Adam ------------------------
+    def symm_alloc(self, n: int):
+        """-> (device pointer, 64-byte IPC handle) of a zero-filled symmetric buffer for n gradient floats."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.check(self.lib.nvf_symm_alloc(self.lib.nvf_symm_bytes(int(n)), C.byref(ptr), handle), "nvf_symm_alloc")
+        return ptr.value, handle.raw
+
+    def symm_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.check(self.lib.nvf_symm_open(C.create_string_buffer(handle, 64), C.byref(ptr)), "nvf_symm_open")
+        return ptr.value
+
+    def symm_close(self, ptr: int) -> None:
+        self.check(self.lib.nvf_symm_close(ptr), "nvf_symm_close")
+
+    def symm_free(self, ptr: int) -> None:
+        self.check(self.lib.nvf_symm_free(ptr), "nvf_symm_free")
+
+    def adam_allreduce_step(self, param, grad, exp_avg, exp_avg_sq, step, lr, peers, rank, ctl, beta1=0.9,
+                            beta2=0.999, eps=1e-8):
+        arr = (C.c_void_p * len(peers))(*peers)
+        rc = self.lib.nvf_adam_allreduce_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq),
+                                              int(param.numel()), _ptr(step), _ptr(lr), float(beta1), float(beta2),
+                                              float(eps), arr, int(rank), len(peers), _ptr(ctl),
+                                              self._stream(param.device))
+        self.check(rc, "nvf_adam_allreduce_step")
 
     # ---- fused weight-loop step -------------------------------------------------------------------
     def train_step_workspace(self, desc: NvfDesc, n: int, dev: torch.device) -> torch.Tensor:

@@ -16,6 +16,7 @@
 #include "nvf_step.cuh"
 #include "nvf_rows_convt.cuh"
 #include "nvf_decode_head.cuh"
+#include "nvf_symm.cuh"
 
 namespace nvf {
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches); shared with nvf_prep.cu
@@ -995,6 +996,83 @@ int nvf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   nvf_launch(fast::k_adam, dim3(grid), dim3(256), (size_t)(0), l.st, p);
   l.post();
   nvf_launch(fast::k_adam_tick, dim3(1), dim3(1), (size_t)(0), l.st, step);
+  l.post();
+  return l.rc;
+}
+
+size_t nvf_symm_bytes(int64_t n) {
+  return (size_t)fast::kSymmHeaderBytes + 2 * sizeof(float) * 4 * (size_t)((n + 3) / 4);
+}
+
+int nvf_symm_alloc(size_t bytes, void** ptr_out, void* handle64_out) {
+  if (!ptr_out || !handle64_out || bytes < (size_t)fast::kSymmHeaderBytes) return NVF_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    g_last_cuda = (int)e;
+    cudaGetLastError();
+    if (p) cudaFree(p);
+    return NVF_ERR_CUDA;
+  }
+  memcpy(handle64_out, &h, 64);
+  *ptr_out = p;
+  return NVF_OK;
+}
+
+int nvf_symm_open(const void* handle64, void** ptr_out) {
+  if (!handle64 || !ptr_out) return NVF_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    g_last_cuda = (int)e;
+    cudaGetLastError();
+    return NVF_ERR_CUDA;
+  }
+  *ptr_out = p;
+  return NVF_OK;
+}
+
+int nvf_symm_close(void* ptr) {
+  if (!ptr) return NVF_ERR_INVALID_ARG;
+  const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { g_last_cuda = (int)e; cudaGetLastError(); return NVF_ERR_CUDA; }
+  return NVF_OK;
+}
+
+int nvf_symm_free(void* ptr) {
+  if (!ptr) return NVF_ERR_INVALID_ARG;
+  const cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { g_last_cuda = (int)e; cudaGetLastError(); return NVF_ERR_CUDA; }
+  return NVF_OK;
+}
+
+int nvf_adam_allreduce_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* step,
+                            const float* lr, float beta1, float beta2, float eps, void* const* peers, int rank,
+                            int world, void* ctl, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || !lr || !peers || !ctl || n <= 0 || n > (1 << 30))
+    return NVF_ERR_INVALID_ARG;
+  if (world < 1 || world > fast::kSymmMaxRanks || rank < 0 || rank >= world) return NVF_ERR_INVALID_ARG;
+  DevLauncher l{(cudaStream_t)stream};
+  if (l.init() != NVF_OK) return l.rc;
+  fast::ArAdamParams p{};
+  p.param = param; p.grad = grad; p.m = exp_avg; p.v = exp_avg_sq; p.step = step; p.lr = lr;
+  p.beta1 = beta1; p.beta2 = beta2; p.eps = eps;
+  p.n = (int32_t)n; p.n4 = (int32_t)((n + 3) / 4);
+  p.rank = rank; p.world = world; p.ctl = (unsigned int*)ctl;
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r]) return NVF_ERR_INVALID_ARG;
+    p.peer[r] = (char*)peers[r];
+  }
+  int grid = (p.n4 + 255) / 256;
+  if (grid > 64) grid = 64;                 // all CTAs resident: the last one to finish its copy publishes
+  if (grid > l.n_sms) grid = l.n_sms;
+  nvf_launch(fast::k_allreduce_adam, dim3(grid), dim3(256), (size_t)(0), l.st, p);
   l.post();
   return l.rc;
 }

@@ -27,6 +27,7 @@ from . import ops
 STAT_NAMES = ("loss", "bce", "ms0", "ms1", "b_latent", "b_net", "n_pts")
 EXPORTS = ("nvf_gather_batch",)          # include/nvf_prep_b200.h entry points bound here
 _gather_bound = None
+_last_opt = None
 
 
 def _gather_batch(emb_all, gt_all, dist_all, idx, emb_out, gt_out, dist_out, status=None) -> None:
@@ -103,6 +104,78 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr_t = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
+        self._symm = None            # peer-mapped gradient buffers (enable_peer_allreduce)
+        self._symm_tried = False
+
+    def enable_peer_allreduce(self) -> bool:
+        """Data parallel with one process per GPU of ONE node (NCCL backend): allocate this rank's symmetric gradient
+        buffer, exchange the CUDA IPC handles and map the peers' buffers, so that step_allreduce() is ONE kernel
+        (nvf_adam_allreduce_step: all-reduce over NVLink fused with Adam) instead of an NCCL all-reduce + Adam.
+        COLLECTIVE: every rank must call it.  Returns False - and the NCCL path stays - when the process group is not
+        NCCL / spans several hosts / has more than 16 ranks, NVF_PEER_ALLREDUCE=0, or any rank could not map its peers
+        (decided by all ranks together; the reason goes to stderr)."""
+        import os, socket, sys
+        import torch.distributed as tdist
+        self._symm_tried = True
+        if not D.is_dist() or os.environ.get("NVF_PEER_ALLREDUCE", "1") == "0":
+            return False
+        if tdist.get_backend() != "nccl":
+            return False
+        rank, ws = D.world()
+        dev = self.flat.device
+        b = ops._lib.cuda_binding()
+        ok, own, handle, why = 1, None, b"", ""
+        if ws > 16:
+            ok, why = 0, "more than 16 ranks"
+        else:
+            try:
+                with torch.cuda.device(dev):
+                    own, handle = b.symm_alloc(self.flat.numel())
+            except ops.NvfError as e:
+                ok, why = 0, str(e)
+        infos = [None] * ws
+        tdist.all_gather_object(infos, (socket.gethostname(), handle if ok else b""))
+        peers = []
+        if ok and len({h for h, _ in infos}) != 1:
+            ok, why = 0, "ranks on several hosts"
+        if ok and not all(len(hd) == 64 for _, hd in infos):
+            ok, why = 0, "a peer could not allocate its buffer"
+        if ok:
+            try:
+                with torch.cuda.device(dev):
+                    for r, (_, hd) in enumerate(infos):
+                        peers.append(own if r == rank else b.symm_open(hd))
+            except ops.NvfError as e:
+                ok, why = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            for r, ptr in enumerate(peers):
+                if r != rank:
+                    b.symm_close(ptr)
+            if own is not None:
+                b.symm_free(own)
+            if rank == 0:
+                print("nvfpcc_b200: peer-memory all-reduce unavailable (%s); using the NCCL all-reduce" % (why or "a peer failed"),
+                      file=sys.stderr)
+            return False
+        self._symm = dict(own=own, peers=peers, rank=rank, ctl=torch.zeros(4, dtype=torch.int32, device=dev))
+        tdist.barrier()
+        return True
+
+    @torch.no_grad()
+    def step_allreduce(self):
+        """Sum flat_grad over the ranks and apply Adam: the fused peer-memory kernel when enabled, else ONE NCCL
+        all-reduce followed by nvf_adam_step.  Single process: plain step."""
+        if self._symm is None:
+            D.allreduce_sum_(self.flat_grad)
+            return self.step(gathered=True)
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        g, sy = self.param_groups[0], self._symm
+        ops._lib.cuda_binding().adam_allreduce_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_t,
+                                                    self.lr_t, sy["peers"], sy["rank"], sy["ctl"], g["betas"][0],
+                                                    g["betas"][1], g["eps"])
 
     def sync_lr(self):
         """Mirror param_groups[0]['lr'] to the device scalar (call outside graph capture)."""
@@ -272,6 +345,8 @@ class WeightStep:
         self.fused = self.fused_opt and net.reconstructor.in_channels <= 4 if fused is None else bool(fused)
         if self.fused and not self.fused_opt:
             raise ValueError("WeightStep(fused=True) needs a FusedAdam optimizer (gradients go to its flat buffer)")
+        if self.fused_opt and D.is_dist() and not opt._symm_tried:
+            opt.enable_peer_allreduce()        # collective: every rank builds its steps in the same order
         self._call = None
         self._idx_src = None           # (emb_all, gt_all, dist_all) of the pending step_indexed call
         self._seed = int(torch.initial_seed() if seed is None else seed)
@@ -308,13 +383,12 @@ class WeightStep:
                            q, status=self.status)
         else:
             self._call.run(self.emb, self.gt, self.dist, None, 0, self.n_pts, self.stats, self.sums, q)
-        D.allreduce_sum_(self.opt.flat_grad)                                  # ONE all-reduce, in place
-        self.opt.step(gathered=True)
+        self.opt.step_allreduce()             # all-reduce of the flat gradient + Adam (one fused kernel over NVLink)
 
     def _reduce_and_step(self):
         if self.fused_opt:
-            D.allreduce_sum_(self.opt.gather_grads())            # ONE all-reduce of the flat shared-weight gradient
-            self.opt.step(gathered=True)
+            self.opt.gather_grads()
+            self.opt.step_allreduce()                            # ONE exchange of the flat shared-weight gradient
         else:
             D.allreduce_grads_(self.net.parameters())
             self.opt.step()
@@ -607,6 +681,8 @@ def fit(net, gt: torch.Tensor, dist_: torch.Tensor, *, epochs: int, batchsize: i
         emb = torch.ones((n_leaf_all, ch, 2, 2, 2), dtype=torch.float32)            # NVFPCC.py:120-122
     emb_local = emb[lo:hi].detach().to(dev, torch.float32).clone().requires_grad_(True)
     opt = FusedAdam(net.parameters(), lr=lr)
+    global _last_opt
+    _last_opt = opt                    # introspection for the multi-GPU check (peer all-reduce on / off)
     opt_emb = torch.optim.Adam([emb_local], lr=lr * wemb)
     sch = torch.optim.lr_scheduler.MultiStepLR(opt, list(milestones), 0.1)
     sch_emb = torch.optim.lr_scheduler.MultiStepLR(opt, list(milestones), 0.1)      # sic: wraps opt (NVFPCC.py:126)

@@ -31,6 +31,7 @@ if rank == 0:
     lat = net.get_latent_code(emb.detach().cuda())["quantized_latent"]
     single = net.decode_points(lat, torch.from_numpy(origins.astype(np.int32)).cuda(), 0.5, return_host=True)["coords"].numpy()
     assert np.array_equal(enc["points"], single) and np.array_equal(dec, single), "sharded reconstruction differs"
+    print("peer all-reduce: %s" % ("on" if getattr(trainer, "_last_opt", None) is not None and trainer._last_opt._symm is not None else "off"))
     print("dist check ok: world %d, bce %.1f -> %.1f, %d points, latent stream %d B" % (
         world, hist[0]["bce"], hist[-1]["bce"], single.shape[0], len(enc["total_pack"]["latent_pack"]["latent_byte_stream"])))
 else:

@@ -178,6 +178,13 @@ int nvf_ffma_microbench(int, int64_t, float*, double*, void*) { return NVF_ERR_N
 int nvf_train_step_workspace_bytes(const NvfDesc*, int64_t, size_t*) { return NVF_ERR_UNSUPPORTED; }
 int nvf_train_step(const NvfStepArgs*, void*, size_t, void*) { return NVF_ERR_UNSUPPORTED; }
 int nvf_rng_uniform(uint64_t, uint64_t, int, int64_t, int64_t, float*, void*) { return NVF_ERR_UNSUPPORTED; }
+size_t nvf_symm_bytes(int64_t) { return 0; }
+int nvf_symm_alloc(size_t, void**, void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_symm_open(const void*, void**) { return NVF_ERR_UNSUPPORTED; }
+int nvf_symm_close(void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_symm_free(void*) { return NVF_ERR_UNSUPPORTED; }
+int nvf_adam_allreduce_step(float*, const float*, float*, float*, int64_t, float*, const float*, float, float, float,
+                            void* const*, int, int, void*, void*) { return NVF_ERR_UNSUPPORTED; }
 
 
 // parameter-side fused kernels exist only in the CUDA library (the torch ops they replace are the CPU reference)
