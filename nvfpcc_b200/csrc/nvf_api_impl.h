@@ -78,7 +78,7 @@ struct DecodeWs {
 };
 
 struct TrainWs {
-  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_p2, off_p1, off_p0, off_loss, off_partial, off_queue, total;
+  size_t off_packed, off_stash, off_grad, off_tmp3, off_tmp1, off_gl2, off_gl1, off_gl0, off_p2, off_p1, off_p0, off_loss, off_partial, off_queue, off_pad, total;
   static TrainWs make(const NvfDesc& d, int64_t n) {
     TrainWs L{};
     const Stash s = Stash::make(d);
@@ -98,6 +98,10 @@ struct TrainWs {
     L.off_loss = take(sizeof(double) * (size_t)NVF_LOSS_SUMS * (n * kLossChunks + 1));
     L.off_partial = take(sizeof(float) * partial_floats(d, n));
     L.off_queue = take(2 * 16 * kQueueSlots);   // forward slots, then backward slots
+    {   // zero-padded copy of the input of a transposed conv (polyphase forward kernels): max over up1 / up2
+      const size_t p1 = (size_t)d.c1 * 8 * 12 * 16, p2 = (size_t)d.c2 * 16 * 20 * 24;
+      L.off_pad = take(sizeof(float) * (p1 > p2 ? p1 : p2) * n);
+    }
     L.total = o;
     return L;
   }
@@ -210,7 +214,7 @@ struct Api {
     // up1: convT k5 s2 p0 + ReLU (:4693-4700, :4762)
     p = LayerParams{a1, a2, packed + g.up1, w.up1_b, nullptr, nullptr, n, d.c1, d.c2, 8, 8, 19, 20, 0, ACT_RELU, OP_CONVT};
     // decode (many leaves): polyphase kernel on a zero-padded copy of conv0's output; else the tile kernels
-    if (!(pad_scratch && l.up1_poly(p, pad_scratch))) layer(l, p);
+    if (!(pad_scratch && l.up_poly(p, pad_scratch))) layer(l, p);
     // conv1: conv k4 + ReLU (:4702-4710, :4763)
     p = LayerParams{a2, a3, packed + g.conv1, w.conv1_b, nullptr, nullptr, n, d.c2, d.c2, 19, 20, 16, 16, 0, ACT_RELU, OP_CORR4};
     layer(l, p);
@@ -227,7 +231,7 @@ struct Api {
     }
     // up2: convT k5 s2 p0 + ReLU (:4712-4719, :4765)
     p = LayerParams{a3, a4, packed + g.up2, w.up2_b, nullptr, nullptr, n, d.c2, d.c3, 16, 16, 35, 36, 0, ACT_RELU, OP_CONVT};
-    layer(l, p);
+    if (!(pad_scratch && l.up_poly(p, pad_scratch))) layer(l, p);
     // conv2: conv k4 + ReLU (:4721-4729, :4766)
     p = LayerParams{a4, a5, packed + g.conv2, w.conv2_b, nullptr, nullptr, n, d.c3, d.c3, 35, 36, 32, 32, 0, ACT_RELU, OP_CORR4};
     layer(l, p);
@@ -362,7 +366,8 @@ struct Api {
     l.set_queue(ws + W.off_queue);
     pack_all(l, *desc, *w, packed, true, true);
     forward_layers(l, *desc, *w, packed, latent, (int)n, (float*)(ws + W.off_stash), out, cls1, cls0,
-                   (float*)(ws + W.off_p2), (float*)(ws + W.off_p1), (float*)(ws + W.off_p0));
+                   (float*)(ws + W.off_p2), (float*)(ws + W.off_p1), (float*)(ws + W.off_p0), false,
+                   l.train_poly() ? (float*)(ws + W.off_pad) : nullptr);
     return l.error();
   }
 

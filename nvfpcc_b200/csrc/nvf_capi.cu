@@ -306,6 +306,12 @@ struct DevLauncher {
     post();
   }
   bool has_head(const NvfDesc& d) { return head_enabled() && head_cfg(d); }
+  // NVF_TRAIN_POLY=0: training forward's up1 / up2 on the tile / row kernels instead of the polyphase kernel (A/B runs)
+  bool train_poly() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("NVF_TRAIN_POLY"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+  }
   void zero_ints(int32_t* p, int64_t n) { chk(cudaMemsetAsync(p, 0, sizeof(int32_t) * (size_t)n, st)); }
   void pad_conv1(const float* src, float* dst, int64_t planes) {
     int64_t grid = (planes * (fast::kSpPlane / 4) + 255) / 256;
@@ -324,15 +330,23 @@ struct DevLauncher {
     nvf_launch(fast::k_pad_in<DIN>, dim3((unsigned)g0), dim3(256), (size_t)0, st, p.in, pad, planes);
     post();
     fast::PolyParams q{pad, p.out, p.Wp, p.bias, p.n};
-    long long grid = (long long)p.n * G::IPL;
+    long long grid = ((long long)p.n * G::WPL + 3) / 4;
     if (grid > (long long)n_sms * G::MINB) grid = (long long)n_sms * G::MINB;
     nvf_launch(k, dim3((unsigned)grid), dim3(128), (size_t)G::SMEM_BYTES, st, q);
     post();
     return true;
   }
-  // up1 of the decode stem (many leaves): polyphase kernel; false = not instantiated for this shape
-  bool up1_poly(const LayerParams& p, float* pad) {
-    if (p.Din != 8 || p.act != ACT_RELU) return false;   // every batch size: a leaf's result must not depend on it
+  // up1 of the decode stem (many leaves) and up1 / up2 of the training forward: polyphase kernel on a zero-padded
+  // copy of the input; false = not instantiated for this shape.  Decode uses it for EVERY batch size (a leaf's result
+  // must not depend on it).
+  bool up_poly(const LayerParams& p, float* pad) {
+    if (p.act != ACT_RELU || p.op != OP_CONVT || p.P != 0) return false;
+    if (p.Din == 16) {
+      if (p.CI == 8 && p.CO == 8) return poly_t<8, 8, 16>(p, pad);
+      if (p.CI == 16 && p.CO == 16) return poly_t<16, 16, 16>(p, pad);
+      return false;
+    }
+    if (p.Din != 8) return false;
     // measured on B200, 1247 leaves, vs the tile kernel: 32 -> 16 channels 5.51 -> 3.73 ms, 16 -> 8 channels 1.28 -> 0.98 ms
     if (p.CI == 32 && p.CO == 16) return poly_t<32, 16, 8>(p, pad);
     if (p.CI == 16 && p.CO == 8) return poly_t<16, 8, 8>(p, pad);
@@ -1244,7 +1258,8 @@ int train_step_impl(DevLauncher& l, const NvfStepArgs& a, void* workspace, size_
   float* p1 = (float*)(tws + T.off_p1);
   float* p0 = (float*)(tws + T.off_p0);
   l.set_queue(tws + T.off_queue);   // zero since the caller's one-time fill; every queue-fed kernel rewinds its words
-  Api<DevLauncher>::forward_layers(l, d, w, (const float*)(tws + T.off_packed), latent, n, (float*)(tws + T.off_stash), p2, p1, p0);
+  Api<DevLauncher>::forward_layers(l, d, w, (const float*)(tws + T.off_packed), latent, n, (float*)(tws + T.off_stash), p2, p1, p0,
+                                   nullptr, nullptr, nullptr, false, l.train_poly() ? (float*)(tws + T.off_pad) : nullptr);
 
   // ---- loss, metrics, dL/dlogit, total loss and scalar cotangents: one launch
   const bool bwd = wg || demb;

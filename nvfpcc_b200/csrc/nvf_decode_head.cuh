@@ -595,24 +595,27 @@ __global__ void __launch_bounds__(256) k_pad_in(const float* __restrict__ src, f
   }
 }
 
-// Stand-alone polyphase k=5 stride-2 transposed conv + ReLU over many leaves (the decode stem's up1): the head
-// producer's thread tile (8 x = 4 even + 4 odd outputs, 8 output channels, all taps of one input channel unrolled)
-// with one warp per (output slice, row parity, channel group).  A CTA of four warps works on one slice (two channel
-// groups) or two adjacent slices (one group) and streams the weights of one input channel at a time through a
-// two-stage cp.async ring, so its shared memory is 2 x 125 x CO floats and several CTAs share an SM.
+// Stand-alone polyphase k=5 stride-2 transposed conv + ReLU (up1 of the decode stem over many leaves; up1 / up2 of
+// the training forward): the head producer's thread tile (8 x = 4 even + 4 odd outputs, 8 output channels) with one
+// WARP ITEM per (leaf, row parity, output slice, channel group, group of RPW rows): up to 32 tiles of equal tap count.
+// Weights stay resident in shared memory when they fit 72 KB - the warps then pull items independently and never
+// meet - else they stream through a two-stage cp.async ring, one input channel at a time, and the four warps of a CTA
+// walk their four consecutive items channel by channel together.
 template <int CI, int CO, int DIN>
 struct PolyCfg {
   static_assert(CO == 8 || CO == 16, "channel groups of 8");
   static constexpr int DOUT = 2 * DIN + 3, OP = (DOUT + 3) / 4 * 4;
   static constexpr int PROWS = DIN + 4, PPITCH = DIN + 8, PPLANE = PROWS * PPITCH;
-  static constexpr int COH = CO / 8, NSL = 2 / COH;        // slices per CTA item
+  static constexpr int COH = CO / 8;
   static constexpr int NE = (DOUT + 1) / 2, NO = DOUT / 2, XT = (DOUT + 7) / 8;
-  static constexpr int IPL = (DOUT + NSL - 1) / NSL;       // items per leaf
+  static constexpr int RPW = 32 / XT;                      // rows of one warp item
+  static constexpr int RG = (NE + RPW - 1) / RPW;          // row groups per (slice, parity)
+  static_assert((NO + RPW - 1) / RPW == RG, "same number of row groups for both parities");
+  static constexpr int WPL = 2 * DOUT * COH * RG;          // warp items per leaf, ordered [parity][slice][group][rows]
   static constexpr int STAGE = 125 * CO;
-  static constexpr bool RING = CI * STAGE * 4 > 72 * 1024;   // else all weights stay resident and the warps never meet
+  static constexpr bool RING = CI * STAGE * 4 > 72 * 1024;
   static constexpr int SMEM_BYTES = (RING ? 2 : CI) * STAGE * 4;
   static constexpr int MINB = RING ? 4 : 3;
-  static_assert(NE * XT <= 32, "one warp per (slice, row parity, channel group)");
 };
 
 struct PolyParams {
@@ -629,12 +632,7 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
   using G = PolyCfg<CI, CO, DIN>;
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int cy = warp >> 1;                                 // row parity of this warp
-  const int coh = G::COH == 2 ? (warp & 1) : 0;
-  const int nrows = cy ? G::NO : G::NE;
-  const bool lane_ok = lane < nrows * G::XT;
-  const int q = lane_ok ? lane % G::XT : 0, rr = lane_ok ? lane / G::XT : 0;
-  const int l = 2 * rr + cy;                                // output row
+  const int q = lane % G::XT, rl = lane / G::XT;            // x tile and row inside the group
   uint32_t ring_step = 0;
   for (int i = tid; i < (G::RING ? 1 : CI) * G::STAGE / 4; i += 128) tma::cp_async16(sm + 4 * i, p.w + 4 * i);
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -642,12 +640,29 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
-  const int total = p.n * G::IPL;
+  const long long total = (long long)p.n * G::WPL;
+  // RING: the CTA's warps take four consecutive items per round (same number of rounds for every warp of the CTA);
+  // resident weights: every warp strides over the items on its own
+  const long long first = (long long)blockIdx.x * 4 + warp, stride = (long long)gridDim.x * 4;
+  const long long rounds = (total + stride - 1) / stride;
 #pragma unroll 1
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int b = item / G::IPL;
-    const int s = (item - b * G::IPL) * G::NSL + (G::NSL == 2 ? (warp & 1) : 0);   // output slice of this warp
-    const bool active = lane_ok && s < G::DOUT;
+  for (long long rd = 0; rd < rounds; ++rd) {
+    const long long wi = first + rd * stride;
+    const bool have = wi < total;
+    if (!G::RING && !have) break;
+    int b = 0, cy = 0, s = 0, coh = 0, rg = 0;
+    if (have) {
+      b = (int)(wi / G::WPL);
+      int r = (int)(wi - (long long)b * G::WPL);
+      rg = r % G::RG; r /= G::RG;
+      coh = r % G::COH; r /= G::COH;
+      s = r % G::DOUT;
+      cy = r / G::DOUT;
+    }
+    const int nrows = cy ? G::NO : G::NE;
+    const int rr = rg * G::RPW + rl;
+    const bool active = have && rl < G::RPW && rr < nrows;
+    const int l = 2 * rr + cy;                              // output row
     // valid kz taps: kz = kz0, kz0+2, .. with 0 <= (s - kz) / 2 <= DIN-1
     int kz0 = s & 1;
     while (s - kz0 > 2 * (DIN - 1)) kz0 += 2;
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[c][j] = p2_bcast(0.f);
     const float* in_t = p.inp + (size_t)b * CI * DIN * G::PPLANE +
-                        ((size_t)((s - kz0) >> 1) * G::PROWS + (((l - cy) >> 1) + 2)) * G::PPITCH + 4 * q + 2;
+                        ((size_t)((s - kz0) >> 1) * G::PROWS + (active ? rr + 2 : 2)) * G::PPITCH + 4 * q + 2;
     const int w_off = ((kz0 * 5 + cy) * 5) * CO + coh * 8;
 #pragma unroll 1
     for (int ci = 0; ci < CI; ++ci) {

@@ -67,7 +67,8 @@ struct EmuLauncher {
   bool has_head(const NvfDesc&) { return false; }
   void zero_ints(int32_t*, int64_t) {}
   void pad_conv1(const float*, float*, int64_t) {}
-  bool up1_poly(const LayerParams&, float*) { return false; }
+  bool up_poly(const LayerParams&, float*) { return false; }
+  bool train_poly() { return false; }
   void head(const NvfDesc&, const HeadArgs&, int) {}
   void side_begin() {}
   void side_end() {}

@@ -147,3 +147,16 @@ def test_empty_inputs():
         grids.build_grids(np.zeros((4, 2), np.int32), np.zeros((1, 3), np.int32))
     with pytest.raises(ValueError):
         grids.build_grids(np.array([[0.5, 1, 2]]), np.zeros((1, 3), np.int32))
+
+
+def test_host_results_equal_device_float64():
+    """build_grids_host (uint16 squared distances to the host, square root on the host cores) returns exactly the
+    float64 distances and uint8 grid the device path writes."""
+    from nvfpcc_b200 import grids, synth
+    pts = synth.sphere_shell_points(256)
+    origins = synth.leaf_origins(pts)[:40]
+    dev = grids.build_grids(pts, origins, want_gt=True, want_dist64=True)
+    host = grids.build_grids_host(pts, origins)
+    assert host["dist"].dtype == np.float64 and host["gt"].dtype == np.uint8
+    assert np.array_equal(host["dist"], dev["dist"].cpu().numpy())
+    assert np.array_equal(host["gt"], dev["gt"].cpu().numpy())
