@@ -432,7 +432,7 @@ def embedding_loop(tw, args, world, n_blocks, flush):
 
 # ----------------------------------------------------------------------------- rows either side of the path
 def measured_traffic(kind, **match):
-    """roofline.traffic: DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), only
+    """roofline.traffic: DRAM bytes per launch from the committed ncu capture (profiles/r02_traffic.json), only
     when this run's workload is the captured one; otherwise None."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -485,7 +485,7 @@ def grids_bench(args, rank, world, pts, origins, flush, with_cpu):
                points=int(pts.shape[0]), gpu_launches=3 * reps, occupied=int(gt_h.sum()) if world == 1 else None,
                workload="gt_grid + dist of all %d leaves of the synthetic cloud (util_get_grids.py), exact, float64" % n_all,
                e2e=dict(value=vox / (e2e_ms * 1e-3), unit="voxels/s", h2d_bytes_per_step=int(pts.shape[0] * 12 + (hi - lo) * 12),
-                        d2h_bytes_per_step=int((hi - lo) * 32768 * 3)),
+                        d2h_bytes_per_step=int((hi - lo) * 32768 * 9)),
                roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                              traffic=measured_traffic("grids", blocks=int(hi - lo)),
                              per_gpu=True, algorithmic_bytes_per_block=32768 * bytes_per_vox, peak_source=src,
@@ -850,7 +850,8 @@ def main():
         ach = w.n_local * F_DEC[chanstr] / (d["ms_kernel"] * 1e-3) / 1e12    # rank 0's blocks / its kernel time
         tr = measured_traffic("decode", chanstr=chanstr, blocks=int(w.n_local))
         return dict(bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=tr,
-                    kernel="k_decode_fused" if binding.has_fused_decode(chanstr) else "layer-wise kernels")
+                    kernel="nvf_decode: stem layer kernels + k_decode_head (fused up2-conv2-cls-threshold, 78 % of the time)"
+                    if binding.has_fused_decode(chanstr) else "layer-wise kernels")
 
     dec["roofline"] = dec_roofline(dec, dw, cs)
     if dec_wide is not None:

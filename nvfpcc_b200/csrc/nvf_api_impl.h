@@ -19,14 +19,17 @@ constexpr int64_t kGenericDecodeChunk = 128;  // blocks per pass of the layer-wi
 // per-leaf scratch of the two-pass (wide) head: conv2 rows next to the cut + their partial logits
 inline size_t head_brow_floats(const NvfDesc& d) { return d.c3 == 16 ? (size_t)2 * d.c3 * 1024 : 0; }
 inline size_t head_pl_floats(const NvfDesc& d) { return d.c3 == 16 ? (size_t)2048 : 0; }
-// blocks per pass of the fused-head decode path: as many whole waves of 148 persistent CTAs as fit 3 GiB of
-// stem activations (8,16,8,8: 0.6 MB per block; 16,32,16,16: 1.2 MB), so a cloud is normally one pass and no SM
-// idles at a chunk boundary
+// blocks per pass of the fused-head decode path: the stem activations of a pass live in the workspace (8,16,8,8:
+// 0.6 MB per block; 16,32,16,16: 1.4 MB), so a cloud is one pass up to 8 GiB of them (vox11 wide: 6.7 GB) and is
+// otherwise cut into EQUAL passes - every pass ends with one partial round of the head kernel, and equal passes keep
+// those few
 inline int64_t head_chunk(const NvfDesc& d, int64_t n) {
   const int64_t per_block = 4 * (Stash::make(d).a4 + (int64_t)d.c2 * 16 * 480 + (int64_t)head_brow_floats(d) + (int64_t)head_pl_floats(d));
-  int64_t c = ((int64_t)3 << 30) / per_block / 148 * 148;
-  if (c < 148) c = 148;
-  return n < c ? n : c;
+  int64_t cmax = ((int64_t)8 << 30) / per_block;
+  if (cmax < 148) cmax = 148;
+  if (n <= cmax) return n;
+  const int64_t passes = (n + cmax - 1) / cmax;
+  return (n + passes - 1) / passes;
 }
 // configurations the warp-specialised fused decode head (nvf_decode_head.cuh) is instantiated for
 inline bool head_cfg(const NvfDesc& d) { return (d.c2 == 8 && d.c3 == 8) || (d.c2 == 16 && d.c3 == 16); }

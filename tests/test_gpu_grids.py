@@ -150,8 +150,7 @@ def test_empty_inputs():
 
 
 def test_host_results_equal_device_float64():
-    """build_grids_host (uint16 squared distances to the host, square root on the host cores) returns exactly the
-    float64 distances and uint8 grid the device path writes."""
+    """build_grids_host (pinned staging buffers) returns exactly the float64 distances and uint8 grid of the device path."""
     from nvfpcc_b200 import grids, synth
     pts = synth.sphere_shell_points(256)
     origins = synth.leaf_origins(pts)[:40]

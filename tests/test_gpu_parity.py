@@ -76,6 +76,23 @@ def test_fused_A_equals_layerwise_A(gpu):
     np.testing.assert_allclose(a["prob"].cpu().numpy(), out.cpu().numpy(), rtol=0, atol=2e-6)
 
 
+def test_fused_B_equals_layerwise_B_and_small_batches_are_cut_along_z(gpu):
+    """chanstr 16,32,16,16 runs through the fused head kernel (two y passes + boundary-row fix-up).  7 leaves = 14
+    (leaf, pass) units on 148 SMs, i.e. every unit is cut into 8 z chunks; 1 leaf = 2 units, also 8 chunks each: the
+    probabilities must equal the layer kernels' (independent implementation) and must not depend on the batch."""
+    assert gpu.has_fused_decode("16,32,16,16") and gpu.has_fused_decode("8,16,8,8")
+    fx = fixture_inputs("B")
+    desc = gpu.desc(fx["ch"], fx["channels"])
+    w = eff_weights(fx["sd"], 2, "cuda")
+    lat = torch.round(torch.randn(7, 3, 2, 2, 2, generator=torch.Generator().manual_seed(12)) * 3).cuda()
+    a = gpu.decode(desc, w, lat, None, 0.5, want_prob=True)
+    out, cls1, cls0, ws, keep = gpu.train_forward(desc, w, lat)
+    np.testing.assert_allclose(a["prob"].cpu().numpy(), out.cpu().numpy(), rtol=0, atol=2e-6)
+    one = gpu.decode(desc, w, lat[3:4], None, 0.5, want_prob=True)
+    assert torch.equal(one["prob"][0], a["prob"][3])
+    assert int(one["counts"][0]) == int(a["counts"][3]) == int((a["prob"][3] > 0.5).sum())
+
+
 def test_train_forward_backward_A(gpu, golden_A):
     check_train_against_oracle(gpu, fixture_inputs("A"), golden_A, dev="cuda")
 
