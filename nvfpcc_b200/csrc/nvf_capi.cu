@@ -663,10 +663,17 @@ struct DevLauncher {
     const int smem = (d.ch * 8 + 2 * d.c0 * 64 + d.c0 * d.c0 + d.c0 + ((d.ch * 125 * d.c0 + 3) & ~3) + d.c0 * 75 * d.c1) *
                      (int)sizeof(float);
     if (smem > 200 * 1024) return false;
-    if (!smem_attr(fast::k_stem_fwd, smem)) return true;
     fast::StemFwdParams q{latent, up0_wp, w.up0_b, w.igdn_beta, w.igdn_gamma, conv0_wp, w.conv0_b,
                           nullptr, nullptr, x0, a0, a1, nullptr, nullptr, n, d.ch, d.c0, d.c1};
-    nvf_launch(fast::k_stem_fwd, dim3(n * 8), dim3(fast::kStemFwdThreads), (size_t)(smem), st, q);
+    const int per_sm = smem > 110 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);   // resident 512-thread CTAs per SM
+    if (n * 8 > n_sms * per_sm * 2) {     // more slice CTAs than two waves: persistent CTAs, weights staged once
+      if (!smem_attr(fast::k_stem_fwd<true>, smem)) return true;
+      int ctas = n_sms * per_sm & ~1;
+      nvf_launch(fast::k_stem_fwd<true>, dim3(ctas), dim3(fast::kStemFwdThreads), (size_t)(smem), st, q);
+    } else {
+      if (!smem_attr(fast::k_stem_fwd<false>, smem)) return true;
+      nvf_launch(fast::k_stem_fwd<false>, dim3(n * 8), dim3(fast::kStemFwdThreads), (size_t)(smem), st, q);
+    }
     post();
     if (cls0) {   // conv0_cls + sigmoid: auxiliary head, off the critical path
       LayerParams p{a1, cls0, cls0_wp, w.cls0_b, nullptr, nullptr, n, d.c1, 1, 8, 8, 8, 8, 1, ACT_SIGMOID, OP_CORR3};

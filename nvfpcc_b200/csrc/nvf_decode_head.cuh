@@ -611,7 +611,7 @@ struct PolyCfg {
   static constexpr int RPW = 32 / XT;                      // rows of one warp item
   static constexpr int RG = (NE + RPW - 1) / RPW;          // row groups per (slice, parity)
   static_assert((NO + RPW - 1) / RPW == RG, "same number of row groups for both parities");
-  static constexpr int WPL = 2 * DOUT * COH * RG;          // warp items per leaf, ordered [parity][slice][group][rows]
+  static constexpr int WPL = 2 * DOUT * COH * RG;          // warp items per leaf, ordered [row parity][slice: even z, then odd z][channel group][row group]
   static constexpr int STAGE = 125 * CO;
   static constexpr bool RING = CI * STAGE * 4 > 72 * 1024;
   static constexpr int SMEM_BYTES = (RING ? 2 : CI) * STAGE * 4;
@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
       int r = (int)(wi - (long long)b * G::WPL);
       rg = r % G::RG; r /= G::RG;
       coh = r % G::COH; r /= G::COH;
-      s = r % G::DOUT;
+      const int j = r % G::DOUT;                            // slices of equal z parity (equal kz tap count) are neighbours,
+      s = j < G::NE ? 2 * j : 2 * (j - G::NE) + 1;          // so the four items a CTA walks in step cost the same
       cy = r / G::DOUT;
     }
     const int nrows = cy ? G::NO : G::NE;

@@ -37,9 +37,15 @@ struct StemFwdParams {
 // convT k5 s2 p2 op1 taps of output coordinate o along one axis: k = (o & 1) + 2t, input (o + 2 - k) / 2
 __device__ __forceinline__ int stem_tap_lo(int o) { return o & 1; }
 
-// grid = n * 8: CTA (b, zs) recomputes the tiny up0 + IGDN and produces conv0's output slice zs;
-// the conv0_cls head runs afterwards as a classifier kernel (nvf_fast_conv.cuh).
+// PERSIST = false (training, few blocks): grid = n * 8, CTA (b, zs) recomputes the tiny up0 + IGDN and produces conv0's
+// output slice zs: 8 short CTAs per block, everything latency-bound runs in parallel.
+// PERSIST = true (decode of a whole cloud): grid = 2 * G, CTA (g, z parity) stages the conv0 taps of its parity ONCE
+// (154 KB at 16,32 channels: re-staging them per slice was 1.9 GB of L2 traffic per 1247 leaves and 3.4 ms), then
+// walks over the leaves g, g+G, ..: up0 + IGDN once per leaf, then the four slices of its parity.  Per output the
+// arithmetic is the same in both modes, so a leaf's result does not depend on the mode.
+// The conv0_cls head runs afterwards as a classifier kernel (nvf_fast_conv.cuh).
 constexpr int kStemFwdThreads = 512;
+template <bool PERSIST>
 __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
   pdl_entry();
   extern __shared__ __align__(128) float smem[];
@@ -50,9 +56,8 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
   float* s_gam = s_a0 + C0 * 64;       // [C0][C0] gamma, then [C0] beta
   float* s_wu = s_gam + C0 * C0 + C0;  // up0 weights [CH][125][C0]
   float* s_wc = s_wu + ((CH * 125 * C0 + 3) & ~3);  // conv0 weights of this slice's kz parity [C0][3][25][C1]
-  const int b = blockIdx.x >> 3, zs = blockIdx.x & 7, tid = threadIdx.x;
-  const int pz = zs & 1, NT = pz ? 2 : 3;              // kz = pz + 2t
-  if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
+  const int tid = threadIdx.x;
+  const int pz = PERSIST ? (blockIdx.x & 1) : (blockIdx.x & 7) & 1, NT = pz ? 2 : 3;   // kz = pz + 2t
   for (int i = tid; i < C0 * C0 + C0; i += kStemFwdThreads) s_gam[i] = i < C0 * C0 ? p.gamma[i] : p.beta[i - C0 * C0];
   for (int i = tid; i < CH * 125 * C0; i += kStemFwdThreads) s_wu[i] = __ldg(p.up0_wp + i);
   {
@@ -64,6 +69,11 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
             __ldg(reinterpret_cast<const float4*>(p.conv0_wp + ((size_t)(ci * 5 + pz + 2 * t) * 25) * C1) + v4);
     }
   }
+  const int b_step = PERSIST ? (int)(gridDim.x >> 1) : p.n;
+#pragma unroll 1
+  for (int b = PERSIST ? (int)(blockIdx.x >> 1) : (int)(blockIdx.x >> 3); b < p.n; b += b_step) {
+  __syncthreads();                                       // weights staged / the previous leaf's activations are free
+  if (tid < CH * 8) s_lat[tid] = p.latent[(size_t)b * CH * 8 + tid];
   __syncthreads();
   // up0: CH x 2^3 -> C0 x 4^3
   for (int idx = tid; idx < C0 * 64; idx += kStemFwdThreads) {
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
         }
       }
     s_x0[idx] = v;
-    if (zs == 0) p.x0[(size_t)b * C0 * 64 + idx] = v;
+    if (PERSIST ? pz == 0 : (blockIdx.x & 7) == 0) p.x0[(size_t)b * C0 * 64 + idx] = v;
   }
   __syncthreads();
   // IGDN
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
     }
     const float v = s_x0[idx] * sqrtf(nn);
     s_a0[idx] = v;
-    if (zs == 0) p.a0[(size_t)b * C0 * 64 + idx] = v;
+    if (PERSIST ? pz == 0 : (blockIdx.x & 7) == 0) p.a0[(size_t)b * C0 * 64 + idx] = v;
   }
   __syncthreads();
   // conv0 slice zs: C0 x 4^3 -> C1 x 8 x 8, ReLU.  item = (position in the slice, group of 4 output channels);
@@ -106,6 +116,8 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
   // this latency-bound kernel) and combined with one shuffle, always in the order (low half) + (high half).
   const int groups = C1 / 4;
   const int half = tid & 1, ci_lo = half * (C0 / 2), ci_hi = ci_lo + C0 / 2;
+#pragma unroll 1
+  for (int zs = PERSIST ? pz : (int)(blockIdx.x & 7); zs < (PERSIST ? 8 : (int)(blockIdx.x & 7) + 1); zs += 2)
   for (int item = tid >> 1; item < 64 * groups; item += kStemFwdThreads / 2) {
     const int pos = item & 63, cg = item >> 6;
     const int z = zs, y = pos >> 3, x = pos & 7;
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(kStemFwdThreads) k_stem_fwd(StemFwdParams p) {
       const float v = (half ? other + acc[c] : acc[c] + other) + p.conv0_b[cg * 4 + c];
       if (half == 0) p.a1[((size_t)b * C1 + cg * 4 + c) * 512 + zs * 64 + pos] = v > 0.f ? v : 0.f;
     }
+  }
   }
 }
 
