@@ -306,12 +306,16 @@ class TrainWorkload:
         if not hasattr(self, "feeder"):
             self.feeder = trainer.HostBatchFeeder(self.gt_host, self.dist_host, self.B)
             self.emb_batches = [self.emb[self.batch_idx(i).cuda()] for i in range(max(1, self.nb // self.B))]
+            # schedule rows (slot's row indices + the batch's n_pts) for the in-place read of the feeder's slots
+            self.packed_e2e = [[self.ws.pack_schedule(self.feeder.slot_rows(s), n) for n in self.npts] for s in range(2)]
         f = self.feeder
         f.submit(self.batch_idx(first))
         for i in range(first, first + steps):
             (gt, dst), slot = f.take()
             k = i % len(self.emb_batches)
-            st = self.ws.step(self.emb_batches[k], gt, dst, q=1, n_pts=self.npts[k])
+            # the fused step reads the slot in place (rows of the feeder's device buffers): no copy of the batch
+            st = self.ws.step_indexed(f.emb_stage(self.emb_batches[k], slot), f.gt_all, f.dist_all, f.slot_rows(slot),
+                                      q=1, n_pts=self.npts[k], packed=self.packed_e2e[slot][k])
             f.release(slot)
             if i + 1 < first + steps:
                 f.submit(self.batch_idx(i + 1))        # overlaps the kernels of step i
@@ -435,7 +439,7 @@ def measured_traffic(kind, **match):
     """roofline.traffic: DRAM bytes per launch from the committed ncu capture (profiles/r02_traffic.json), only
     when this run's workload is the captured one; otherwise None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             e = json.load(f)[kind]
         return e["dram_bytes"] if all(e.get(k) == v for k, v in match.items()) else None
     except Exception:

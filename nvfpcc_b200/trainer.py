@@ -541,8 +541,15 @@ class HostBatchFeeder:
         shape = (batch,) + tuple(gt_host.shape[1:])
         self.pin = [(torch.empty(shape, dtype=gt_host.dtype).pin_memory(), torch.empty(shape, dtype=dist_host.dtype).pin_memory())
                     for _ in range(2)]
-        self.dev = [(torch.empty(shape, dtype=torch.float32, device=dev), torch.empty(shape, dtype=torch.float32, device=dev))
-                    for _ in range(2)]
+        # the two device slots are the halves of ONE [2 * batch] tensor per input, so that the fused step can read a
+        # slot in place as rows of a resident "dataset" (WeightStep.step_indexed with slot_rows(slot)): no copy of the
+        # batch into the step's static buffers
+        self.batch = int(batch)
+        self.gt_all = torch.empty((2 * batch,) + tuple(gt_host.shape[1:]), dtype=torch.float32, device=dev)
+        self.dist_all = torch.empty((2 * batch,) + tuple(gt_host.shape[1:]), dtype=torch.float32, device=dev)
+        self.dev = [(self.gt_all[s * batch:(s + 1) * batch], self.dist_all[s * batch:(s + 1) * batch]) for s in range(2)]
+        self._rows = [torch.arange(s * batch, (s + 1) * batch, dtype=torch.int64, device=dev) for s in range(2)]
+        self.emb_all = None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
@@ -573,6 +580,19 @@ class HostBatchFeeder:
         torch.cuda.current_stream().wait_event(self.ready[s])
         self._tail += 1
         return self.dev[s], s
+
+    def slot_rows(self, slot: int) -> torch.Tensor:
+        """Row indices (int64, device) of `slot` inside gt_all / dist_all / emb_stage()."""
+        return self._rows[slot]
+
+    def emb_stage(self, emb_batch: torch.Tensor, slot: int) -> torch.Tensor:
+        """Copy the batch's embedding rows (device tensor, 96 bytes per block) next to the slot's gt / dist rows and
+        return the [2 * batch, ...] staging tensor, so that one index vector addresses all three inputs."""
+        if self.emb_all is None:
+            self.emb_all = torch.zeros((2 * self.batch,) + tuple(emb_batch.shape[1:]), dtype=torch.float32,
+                                       device=self.gt_all.device)
+        self.emb_all[slot * self.batch:(slot + 1) * self.batch].copy_(emb_batch.detach(), non_blocking=True)
+        return self.emb_all
 
     def release(self, slot: int) -> None:
         """Call after the consumer of `slot` has been enqueued on the compute stream."""

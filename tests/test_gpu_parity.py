@@ -53,6 +53,30 @@ def test_decode_many_blocks_deterministic_and_batch_invariant(gpu):
     assert torch.equal(one["coords"], a["coords"][s:s + int(a["counts"][7])])
 
 
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_decode_tail_splitting_is_invisible(gpu, tag):
+    """The fused head cuts the (leaf, pass) units of the last partial round of 148 CTAs along z into 8, 4 or 2 chunks
+    (or leaves them whole).  Whatever the batch size does to a leaf - whole unit, or any chunking - its probabilities,
+    mask and count must be bit-identical: decode the same 160 latents in batches whose tails hit every case."""
+    fx = fixture_inputs(tag)
+    desc = gpu.desc(fx["ch"], fx["channels"])
+    w = eff_weights(fx["sd"], 2, "cuda")
+    units = 1 if tag == "A" else 2                          # passes per leaf
+    g = torch.Generator().manual_seed(5)
+    lat = torch.round(torch.randn(160, 3, 2, 2, 2, generator=g) * 3).cuda()
+    ref = gpu.decode(desc, w, lat, None, 0.5, want_prob=True)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    # leaves in the tail round -> chunks per unit: <= sms/8 units -> 8, <= sms/4 -> 4, <= sms/2 -> 2, more -> 1
+    for n in sorted({1, sms // (8 * units), sms // (4 * units), sms // (2 * units), sms // units - 3,
+                     sms // units + 1, sms // units + sms // (4 * units), 160}):
+        if n < 1 or n > 160:
+            continue
+        r = gpu.decode(desc, w, lat[:n], None, 0.5, want_prob=True)
+        assert torch.equal(r["prob"], ref["prob"][:n]), (tag, n)
+        assert torch.equal(r["counts"], ref["counts"][:n]) and torch.equal(r["mask"], ref["mask"][:n]), (tag, n)
+        assert torch.equal(r["counts"].long(), (r["prob"] > 0.5).flatten(1).sum(1)), (tag, n)
+
+
 def test_decode_empty_and_cap_overflow(gpu):
     fx = fixture_inputs("A")
     desc = gpu.desc(fx["ch"], fx["channels"])
@@ -449,5 +473,22 @@ def test_host_batch_feeder_equals_direct_steps(gpu, golden_A):
             got.append(prev.clone())
     got.append(f.drain().clone())
     assert len(got) == len(order)
+    for a, b in zip(got, direct):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-6, atol=1e-7)
+    # the same batches read IN PLACE from the feeder's device slots (rows of its [2 * batch] buffers)
+    net, ws = _make_fused_step(True)
+    f = trainer.HostBatchFeeder(gt_all, dist_all, 2)
+    got = []
+    f.submit(order[0])
+    for k in range(len(order)):
+        (g, d), slot = f.take()
+        st = ws.step_indexed(f.emb_stage(emb, slot), f.gt_all, f.dist_all, f.slot_rows(slot), q=2)
+        f.release(slot)
+        if k + 1 < len(order):
+            f.submit(order[k + 1])
+        prev = f.read_stats(st)
+        if prev is not None:
+            got.append(prev.clone())
+    got.append(f.drain().clone())
     for a, b in zip(got, direct):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-6, atol=1e-7)
