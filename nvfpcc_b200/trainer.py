@@ -345,6 +345,7 @@ class WeightStep:
         self.fused = self.fused_opt and net.reconstructor.in_channels <= 4 if fused is None else bool(fused)
         if self.fused and not self.fused_opt:
             raise ValueError("WeightStep(fused=True) needs a FusedAdam optimizer (gradients go to its flat buffer)")
+        self._warming = False           # graph-capture warm-up runs: no collectives (see _capture)
         if self.fused_opt and D.is_dist() and not opt._symm_tried:
             opt.enable_peer_allreduce()        # collective: every rank builds its steps in the same order
         self._call = None
@@ -364,7 +365,8 @@ class WeightStep:
             return self._body_fused(q, ext_npts, indexed)
         self.opt.zero_grad(set_to_none=True)
         loss, stats, sums = _loss_terms(self.net, self.emb, self.gt, self.dist, q,
-                                        n_pts=self.n_pts if ext_npts else None, **self.hp)
+                                        n_pts=self.n_pts if ext_npts else (self.gt.sum() if self._warming else None),
+                                        **self.hp)
         loss.backward()
         self._reduce_and_step()
         self.stats.copy_(stats)
@@ -376,21 +378,29 @@ class WeightStep:
             self._call = FusedStepCall(self.net, self.emb.shape[0], hp["n_total"], hp["lmbda"], hp["w1"], hp["w2"],
                                        hp["focal_alpha"], self.opt, self.emb.device, seed=self._seed)
         if not ext_npts:
-            self.n_pts.copy_(D.allreduce_sum_(self.gt.sum()).reshape(1))      # batch-global (NVFPCC.py:154,161)
+            n = self.gt.sum()
+            self.n_pts.copy_((n if self._warming else D.allreduce_sum_(n)).reshape(1))   # batch-global (NVFPCC.py:154,161)
         if indexed:
             emb_all, gt_all, dist_all = self._idx_src
             self._call.run(emb_all, gt_all, dist_all, self._idx_buf, gt_all.shape[0], self.n_pts, self.stats, self.sums,
                            q, status=self.status)
         else:
             self._call.run(self.emb, self.gt, self.dist, None, 0, self.n_pts, self.stats, self.sums, q)
-        self.opt.step_allreduce()             # all-reduce of the flat gradient + Adam (one fused kernel over NVLink)
+        if self._warming:
+            self.opt.step(gathered=True)
+        else:
+            self.opt.step_allreduce()         # all-reduce of the flat gradient + Adam (one fused kernel over NVLink)
 
     def _reduce_and_step(self):
         if self.fused_opt:
             self.opt.gather_grads()
-            self.opt.step_allreduce()                            # ONE exchange of the flat shared-weight gradient
+            if self._warming:
+                self.opt.step(gathered=True)
+            else:
+                self.opt.step_allreduce()                        # ONE exchange of the flat shared-weight gradient
         else:
-            D.allreduce_grads_(self.net.parameters())
+            if not self._warming:
+                D.allreduce_grads_(self.net.parameters())
             self.opt.step()
 
     def empty_step(self) -> torch.Tensor:
@@ -411,8 +421,16 @@ class WeightStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             state = self._snapshot()
-            for _ in range(3):                                   # warm-up: allocator, lazy init, kernel attributes
-                self._body(q, ext_npts, indexed)
+            # warm-up (allocator, lazy init, kernel attributes) WITHOUT the collectives: a rank captures a graph the
+            # first time it meets a (batch size, q) pair, which need not be the step at which its peers do (uneven
+            # shards, short last batches) - every rank must still issue exactly one gradient exchange per global
+            # step.  The state is restored afterwards, so a local Adam update is as good as the real one here.
+            self._warming = True
+            try:
+                for _ in range(3):
+                    self._body(q, ext_npts, indexed)
+            finally:
+                self._warming = False
             self._restore(state)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()

@@ -11,7 +11,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 pts = synth.sphere_shell_points(256)
-origins = synth.leaf_origins(pts)[:50]
+origins = synth.leaf_origins(pts)[:63]      # 32 + 31 leaves: rank 1 meets a new batch size (15) at a step where rank 0 replays
 g = grids.build_grids(pts, origins, want_dist32=True)
 network.set_seed(synth.synthetic_seed()); torch.manual_seed(0)
 net = network.Net(None, "Gaussian", ch=3, channel_str="8,16,8,8").cuda()
