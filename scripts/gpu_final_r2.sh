@@ -3,7 +3,8 @@
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q ) > gpurun_out/r2_pytest_gpu.log 2>&1
 tail -4 gpurun_out/r2_pytest_gpu.log | head -2
-python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 tail -c 600 gpurun_out/r2_bench_n1.json; echo
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
 head -c 400 gpurun_out/r2_bench_reference.json; echo
