@@ -3,6 +3,7 @@
 // (tests/emu/nvf_emu.cpp) execute the same sequencing, workspace layouts and
 // weight packing.
 #pragma once
+#include <stdlib.h>
 #include "../../include/nvf_b200.h"
 #include "nvf_common.h"
 #include "nvf_decode_fused.h"
@@ -27,6 +28,10 @@ inline int64_t head_chunk(const NvfDesc& d, int64_t n) {
   const int64_t per_block = 4 * (Stash::make(d).a4 + (int64_t)d.c2 * 16 * 480 + (int64_t)head_brow_floats(d) + (int64_t)head_pl_floats(d));
   int64_t cmax = ((int64_t)8 << 30) / per_block;
   if (cmax < 148) cmax = 148;
+  if (const char* e = getenv("NVF_DECODE_PASS_LEAVES")) {   // tests: force several passes on a small cloud
+    const long v = atol(e);
+    if (v > 0) cmax = v;
+  }
   if (n <= cmax) return n;
   const int64_t passes = (n + cmax - 1) / cmax;
   return (n + passes - 1) / passes;

@@ -320,6 +320,16 @@ __global__ void k_rd_total(RdTotalParams p) {
 // `step` is a device counter (float, like torch's capturable state) incremented by the kernel,
 // `lr` a device scalar, so that a captured CUDA graph follows LR schedules.
 // ---------------------------------------------------------------------------
+// One element's update with every rounding spelled out (no compiler-chosen FMA contraction), so that k_adam and the
+// fused all-reduce + Adam kernel (nvf_symm.cuh) produce bit-identical parameters from the same gradient.
+__device__ __forceinline__ void adam_update(float& param, float& m, float& v, float g, float beta1, float beta2, float eps,
+                                            float step_size, float bc2s) {
+  m = __fmaf_rn(1.f - beta1, g - m, m);
+  v = __fmaf_rn(1.f - beta2, __fmul_rn(g, g), __fmul_rn(v, beta2));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
+  param = __fmaf_rn(-step_size, __fdiv_rn(m, denom), param);
+}
+
 struct AdamParams {
   float* param; const float* grad; float* m; float* v;
   float* step; const float* lr;
@@ -334,13 +344,10 @@ __global__ void __launch_bounds__(256) k_adam(AdamParams p) {
   const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
   const float step_size = (float)((double)p.lr[0] / bc1), bc2s = (float)sqrt(bc2);
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * 256) {
-    const float g = p.grad[i];
-    float m = p.m[i], v = p.v[i];
-    m = m + (1.f - p.beta1) * (g - m);
-    v = v * p.beta2 + (1.f - p.beta2) * (g * g);
+    float m = p.m[i], v = p.v[i], w = p.param[i];
+    adam_update(w, m, v, p.grad[i], p.beta1, p.beta2, p.eps, step_size, bc2s);
     p.m[i] = m; p.v[i] = v;
-    const float denom = sqrtf(v) / bc2s + p.eps;
-    p.param[i] = p.param[i] - step_size * (m / denom);
+    p.param[i] = w;
   }
 }
 // the counter is advanced by a separate one-thread launch so every CTA of k_adam sees the same t

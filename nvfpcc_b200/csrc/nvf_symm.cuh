@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nvf_common.h"
+#include "nvf_fast_latent.cuh"   // adam_update
 
 namespace nvf {
 namespace fast {
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(ArAdamParams p) {
   const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
   const float step_size = (float)((double)p.lr[0] / bc1), bc2s = (float)sqrt(bc2);
   for (int i = blockIdx.x * 256 + tid; i < p.n4; i += gridDim.x * 256) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.world; ++r) {
+    float4 g = ld_volatile_f4(reinterpret_cast<const float4*>(p.peer[0] + kSymmHeaderBytes) + boff + i);
+    for (int r = 1; r < p.world; ++r) {
       const float4 q = ld_volatile_f4(reinterpret_cast<const float4*>(p.peer[r] + kSymmHeaderBytes) + boff + i);
       g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
     }
@@ -107,12 +108,10 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(ArAdamParams p) {
     for (int j = 0; j < 4; ++j) {
       const int e = 4 * i + j;
       if (e >= p.n) break;
-      float m = p.m[e], v = p.v[e];
-      m = m + (1.f - p.beta1) * (gv[j] - m);
-      v = v * p.beta2 + (1.f - p.beta2) * (gv[j] * gv[j]);
+      float m = p.m[e], v = p.v[e], w = p.param[e];
+      adam_update(w, m, v, gv[j], p.beta1, p.beta2, p.eps, step_size, bc2s);
       p.m[e] = m; p.v[e] = v;
-      const float denom = sqrtf(v) / bc2s + p.eps;
-      p.param[e] = p.param[e] - step_size * (m / denom);
+      p.param[e] = w;
     }
   }
   // 5. the last CTA to finish advances the sequence number and Adam's step counter

@@ -77,6 +77,23 @@ def test_decode_tail_splitting_is_invisible(gpu, tag):
         assert torch.equal(r["counts"].long(), (r["prob"] > 0.5).flatten(1).sum(1)), (tag, n)
 
 
+def test_decode_in_several_passes_equals_one_pass(gpu, monkeypatch):
+    """A cloud whose stem activations exceed the workspace budget is decoded in equal passes (own stem launches, own
+    head launch, own partial round each): force 4 passes on 333 leaves and compare with the single pass."""
+    fx = fixture_inputs("B")
+    desc = gpu.desc(fx["ch"], fx["channels"])
+    w = eff_weights(fx["sd"], 2, "cuda")
+    g = torch.Generator().manual_seed(9)
+    lat = torch.round(torch.randn(333, 3, 2, 2, 2, generator=g) * 3).cuda()
+    org = (torch.arange(333 * 3, dtype=torch.int32).reshape(333, 3) * 32).cuda()
+    one = gpu.decode(desc, w, lat, org, 0.5, want_prob=True)
+    monkeypatch.setenv("NVF_DECODE_PASS_LEAVES", "100")
+    four = gpu.decode(desc, w, lat, org, 0.5, want_prob=True)
+    monkeypatch.delenv("NVF_DECODE_PASS_LEAVES")
+    assert torch.equal(one["prob"], four["prob"]) and torch.equal(one["coords"], four["coords"])
+    assert torch.equal(one["counts"], four["counts"]) and torch.equal(one["mask"], four["mask"])
+
+
 def test_decode_empty_and_cap_overflow(gpu):
     fx = fixture_inputs("A")
     desc = gpu.desc(fx["ch"], fx["channels"])
@@ -357,6 +374,32 @@ def test_fused_adam_matches_torch_adam(gpu):
         for a, b in zip(pa, pb):
             np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
     assert ob.param_groups[0]["lr"] == oa.param_groups[0]["lr"] == pytest.approx(1e-5)
+
+
+def test_allreduce_adam_single_rank_equals_adam_step(gpu):
+    """nvf_adam_allreduce_step with world = 1 (the rank's own symmetric buffer is the only peer: copy, publish, wait
+    and the rank-order sum all run) is bit-identical to nvf_adam_step over several steps, for a size that is not a
+    multiple of four, and leaves the step counter and the sequence number in step."""
+    n = 52219
+    g = torch.Generator(device="cuda").manual_seed(21)
+    pa = torch.randn(n, device="cuda", generator=g)
+    pb = pa.clone()
+    ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+    ta, tb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    lr = torch.full((1,), 1e-3, device="cuda")
+    own, handle = gpu.symm_alloc(n)
+    assert len(handle) == 64
+    ctl = torch.zeros(4, dtype=torch.int32, device="cuda")
+    try:
+        for it in range(5):
+            grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** (it - 2))
+            gpu.adam_step(pa, grad, ma, va, ta, lr)
+            gpu.adam_allreduce_step(pb, grad, mb, vb, tb, lr, [own], 0, ctl)
+            assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and torch.equal(ta, tb)
+        assert int(ctl[0]) == 5 and int(ctl[1]) == 0 and int(ctl[2]) == 0
+    finally:
+        torch.cuda.synchronize()
+        gpu.symm_free(own)
 
 
 def _make_fused_step(graph):
