@@ -331,9 +331,9 @@ struct DevLauncher {
     nvf_launch(fast::k_pad_in<DIN>, dim3((unsigned)g0), dim3(256), (size_t)0, st, p.in, pad, planes);
     post();
     fast::PolyParams q{pad, p.out, p.Wp, p.bias, p.n};
-    long long grid = ((long long)p.n * G::WPL + 3) / 4;
+    long long grid = ((long long)p.n * G::WPL + G::WARPS - 1) / G::WARPS;
     if (grid > (long long)n_sms * G::MINB) grid = (long long)n_sms * G::MINB;
-    nvf_launch(k, dim3((unsigned)grid), dim3(128), (size_t)G::SMEM_BYTES, st, q);
+    nvf_launch(k, dim3((unsigned)grid), dim3(G::THREADS), (size_t)G::SMEM_BYTES, st, q);
     post();
     return true;
   }

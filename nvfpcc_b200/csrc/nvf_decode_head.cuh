@@ -615,7 +615,10 @@ struct PolyCfg {
   static constexpr int STAGE = 125 * CO;
   static constexpr bool RING = CI * STAGE * 4 > 72 * 1024;
   static constexpr int SMEM_BYTES = (RING ? 2 : CI) * STAGE * 4;
-  static constexpr int MINB = RING ? 4 : 3;
+  // resident weights: 8 independent warps share one copy of the weights, two CTAs (16 warps, 128 registers) per SM;
+  // ring: four lock-step warps per CTA, four CTAs per SM
+  static constexpr int THREADS = RING ? 128 : 256, WARPS = THREADS / 32;
+  static constexpr int MINB = RING ? 4 : 2;
 };
 
 struct PolyParams {
@@ -627,14 +630,14 @@ struct PolyParams {
 };
 
 template <int CI, int CO, int DIN>
-__global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_poly(PolyParams p) {
+__global__ void __launch_bounds__((PolyCfg<CI, CO, DIN>::THREADS), (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_poly(PolyParams p) {
   pdl_entry();
   using G = PolyCfg<CI, CO, DIN>;
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = lane % G::XT, rl = lane / G::XT;            // x tile and row inside the group
   uint32_t ring_step = 0;
-  for (int i = tid; i < (G::RING ? 1 : CI) * G::STAGE / 4; i += 128) tma::cp_async16(sm + 4 * i, p.w + 4 * i);
+  for (int i = tid; i < (G::RING ? 1 : CI) * G::STAGE / 4; i += G::THREADS) tma::cp_async16(sm + 4 * i, p.w + 4 * i);
   asm volatile("cp.async.commit_group;" ::: "memory");
   if (!G::RING) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
   const long long total = (long long)p.n * G::WPL;
   // RING: the CTA's warps take four consecutive items per round (same number of rounds for every warp of the CTA);
   // resident weights: every warp strides over the items on its own
-  const long long first = (long long)blockIdx.x * 4 + warp, stride = (long long)gridDim.x * 4;
+  const long long first = (long long)blockIdx.x * G::WARPS + warp, stride = (long long)gridDim.x * G::WARPS;
   const long long rounds = (total + stride - 1) / stride;
 #pragma unroll 1
   for (long long rd = 0; rd < rounds; ++rd) {
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(128, (PolyCfg<CI, CO, DIN>::MINB)) k_convT5_po
         const int nci = ci + 1 < CI ? ci + 1 : 0;
         float* dst = sm + ((ring_step + 1) & 1) * G::STAGE;
         const float* src = p.w + (size_t)nci * G::STAGE;
-        for (int i = tid; i < G::STAGE / 4; i += 128) tma::cp_async16(dst + 4 * i, src + 4 * i);
+        for (int i = tid; i < G::STAGE / 4; i += G::THREADS) tma::cp_async16(dst + 4 * i, src + 4 * i);
         asm volatile("cp.async.commit_group;" ::: "memory");
         w_c = sm + (ring_step & 1) * G::STAGE + w_off;
         ++ring_step;
