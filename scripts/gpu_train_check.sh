@@ -2,8 +2,6 @@
 # quick check after a train-path change: parity tests, bench line, concurrent timeline of one step
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity2.py tests/test_gpu_step.py tests/test_gpu_fit.py -x -q -k "train or step or fit or adam or weight or feeder" ) 2>&1 | tail -2
-for v in 0 1; do
-  NVF_DGRAD_SPLIT=$v python bench.py --skip-prep --skip-wide --skip-epoch --skip-cpu-baseline --steps 30 2>/dev/null | head -c 230; echo
-done
+python bench.py --skip-prep --skip-wide --skip-epoch --skip-cpu-baseline --steps 30 2>/dev/null | head -c 230; echo
 python scripts/timeline.py --out gpurun_out/r2_timeline_latest.txt > /dev/null 2>&1
-grep -E "dgrad" gpurun_out/r2_timeline_latest.txt | cut -c1-110
+head -1 gpurun_out/r2_timeline_latest.txt
