@@ -330,6 +330,23 @@ __device__ __forceinline__ void adam_update(float& param, float& m, float& v, fl
   param = __fmaf_rn(-step_size, __fdiv_rn(m, denom), param);
 }
 
+// Bias corrections in double, like the Python scalars of torch's (non-capturable) Adam: step_size = lr / (1 - b1^t),
+// bc2s = sqrt(1 - b2^t) with t = step + 1.  ONE thread of the CTA evaluates the two double-precision pow() calls (they
+// were most of the kernel's time when every thread did) and hands the floats over through shared memory.
+__device__ __forceinline__ void adam_bias_corrections(const float* step, const float* lr, float beta1, float beta2,
+                                                      float& step_size, float& bc2s) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)step[0] + 1.0;
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    s_bc[0] = (float)((double)lr[0] / bc1);
+    s_bc[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  step_size = s_bc[0];
+  bc2s = s_bc[1];
+}
+
 struct AdamParams {
   float* param; const float* grad; float* m; float* v;
   float* step; const float* lr;
@@ -339,10 +356,8 @@ struct AdamParams {
 
 __global__ void __launch_bounds__(256) k_adam(AdamParams p) {
   pdl_entry();
-  // bias corrections in double, like the Python scalars of torch's (non-capturable) Adam
-  const double t = (double)p.step[0] + 1.0;
-  const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
-  const float step_size = (float)((double)p.lr[0] / bc1), bc2s = (float)sqrt(bc2);
+  float step_size, bc2s;
+  adam_bias_corrections(p.step, p.lr, p.beta1, p.beta2, step_size, bc2s);
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * 256) {
     float m = p.m[i], v = p.v[i], w = p.param[i];
     adam_update(w, m, v, p.grad[i], p.beta1, p.beta2, p.eps, step_size, bc2s);

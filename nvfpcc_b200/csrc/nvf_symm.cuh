@@ -8,7 +8,8 @@
 // and ONE kernel per step does, on every rank:
 //   1. copy the rank's flat gradient into its own copy (seq & 1);
 //   2. when the last CTA has finished copying: store.release.sys `seq` into flag[rank] of EVERY peer's buffer;
-//   3. wait until all flags of the own buffer have reached `seq` (ld.acquire.sys): every peer's copy is complete;
+//   3. wait until all flags of the own buffer have reached `seq` (volatile polls + one acquire fence): every peer's
+//      copy is complete;
 //   4. read all W copies over NVLink (volatile 128-bit loads, 7 x 0.2 MB per rank), add them in rank order
 //      0..W-1 - the same order on every rank, so the weights stay bit-identical across ranks - and apply Adam to
 //      the rank's replica of the weights in the same pass.
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(ArAdamParams p) {
   const unsigned int seq = *(volatile unsigned int*)p.ctl + 1u;
   const size_t boff = (size_t)(seq & 1u) * p.n4;
   __shared__ unsigned int s_last;
+  float step_size, bc2s;            // evaluated (one thread) while the copies are in flight
+  adam_bias_corrections(p.step, p.lr, p.beta1, p.beta2, step_size, bc2s);
   // 1. own gradient -> own symmetric copy (tail of the last float4 zero-filled)
   {
     float4* own = reinterpret_cast<float4*>(p.peer[p.rank] + kSymmHeaderBytes) + boff;
@@ -87,16 +90,16 @@ __global__ void __launch_bounds__(256) k_allreduce_adam(ArAdamParams p) {
     if (tid == 0) p.ctl[1] = 0u;
   }
   // 3. all peers have published this step
+  // (the flags live in THIS rank's memory, so polling reads the local L2 - a relaxed volatile load per poll, one
+  // system-scope acquire fence once the flag is there, instead of an acquire at system scope per poll)
   if (tid < p.world) {
-    const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer[p.rank]) + tid;
-    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+    const volatile unsigned int* f = reinterpret_cast<const volatile unsigned int*>(p.peer[p.rank]) + tid;
+    while ((int)(*f - seq) < 0) {
     }
+    __threadfence_system();
   }
   __syncthreads();
   // 4. sum in rank order + Adam (same arithmetic as k_adam)
-  const double t = (double)p.step[0] + 1.0;
-  const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
-  const float step_size = (float)((double)p.lr[0] / bc1), bc2s = (float)sqrt(bc2);
   for (int i = blockIdx.x * 256 + tid; i < p.n4; i += gridDim.x * 256) {
     float4 g = ld_volatile_f4(reinterpret_cast<const float4*>(p.peer[0] + kSymmHeaderBytes) + boff + i);
     for (int r = 1; r < p.world; ++r) {
