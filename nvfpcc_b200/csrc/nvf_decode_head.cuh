@@ -8,12 +8,14 @@
 //   * producers compute one up2 slice (z fixed, all rows of the pass, all output channels) at a time into a
 //     double-buffered shared-memory slice: polyphase stride-2 transposed conv, 8 x (4 even + 4 odd) outputs x 8
 //     channels per thread, even rows first then odd rows so every warp's tap count is uniform; input rows come
-//     straight from global memory (L1 / L2 resident, one step prefetched in registers).  For the wide configuration
+//     straight from global memory (L1 / L2 resident; all taps of an input channel are unrolled, so the loads of later
+//     taps are issued under the FFMA2s of earlier ones).  For the wide configuration
 //     the 128 KB of up2 weights do not fit next to the slices: they stream through a two-stage cp.async ring, one
 //     input channel (8 KB) per step;
 //   * consumers run conv2 "input-stationary" along z as the round-1 kernel did: slice z of up2 contributes to the
-//     four output slices z-3..z whose partial sums live in registers (4 slices x 8 channels x 4 x = 128
-//     accumulators per thread, FFMA2 over channel pairs); a finished conv2 slice goes to shared memory once and is
+//     four output slices z-3..z whose partial sums live in registers (8 channels x 4 x per slice, FFMA2 over
+//     channel pairs; the oldest slice is finished and written out before the other three are touched, so 96, not
+//     128, accumulators are live at a time); a finished conv2 slice goes to shared memory once and is
 //     consumed the same way by the 3x3x3 classifier; probabilities are thresholded into mask words with warp
 //     shuffles (no shared-memory atomics).
 //   Producer and consumer meet only at the full / empty mbarriers of the two slice buffers, so the transposed conv of
